@@ -1,0 +1,149 @@
+// K2 — diagonal temporal filter (Classic+/++) fused with the future-cost power:
+//     D2[a,b] = sum_k w[k] * D1[a*s + k, b*s + k]          (classic/computeD2.py:34-42)
+//     D3      = D2 ** p                                     (classic/q_learning.py:34)
+// HBM-bound: reads 4 N^2 B (every D1 row is touched), writes 4 M^2 (+4 M^2) B.
+//
+// The reference runs a dense fs x fs cuDNN convolution whose kernel is 97.5 % zeros.  Here one thread
+// walks ONE input diagonal and keeps R consecutive outputs of that diagonal in registers, so it
+// issues (R-1)*s + fs loads for R outputs instead of R*fs, and the taps are compile-time indexed
+// kernel parameters (constant-bank FFMA operands: no shared-memory or LDS traffic at all).  Within
+// a warp consecutive threads own consecutive diagonals, so every load is a coalesced row segment.
+#include "common.cuh"
+
+namespace {
+
+constexpr int FT = 128;      // threads per CTA = diagonals per CTA
+constexpr int FR = 8;        // outputs per thread along its diagonal
+
+struct Taps64 { float w[64]; };
+struct TapsBig { float w[960]; };
+
+template <int FS, int S>
+__global__ void __launch_bounds__(FT)
+diag_filter_kernel(const float *__restrict__ D1, int64_t ld1, int64_t in_row0, int64_t in_rows, const Taps64 taps,
+                   int64_t a0, int64_t rows_out, int64_t m, float *__restrict__ D2, int64_t ld2,
+                   float *__restrict__ D3, int64_t ld3, float p, double *sum, unsigned long long *nnz) {
+    __shared__ double sred[32];
+    __shared__ unsigned long long nred[32];
+    const int64_t n_in = (m - 1) * S + FS;                                  // valid input rows / cols
+    const int64_t a_base = a0 + int64_t(blockIdx.y) * FR;                   // first output row of the band
+    const int64_t b0 = int64_t(blockIdx.x) * FT + threadIdx.x - (FR - 1);   // output col of output 0
+    const int64_t grow = a_base * S;                                        // global input row at t = 0
+    const int64_t gcol = b0 * S;
+    const float *src = D1 + (grow - in_row0) * ld1 + gcol;
+    float acc[FR];
+#pragma unroll
+    for (int i = 0; i < FR; ++i) acc[i] = 0.f;
+    constexpr int T = (FR - 1) * S + FS;
+#pragma unroll
+    for (int t = 0; t < T; ++t) {
+        const bool ok = (gcol + t >= 0) && (gcol + t < n_in) && (grow + t < in_row0 + in_rows);
+        const float x = ok ? __ldg(src + int64_t(t) * (ld1 + 1)) : 0.f;
+#pragma unroll
+        for (int i = 0; i < FR; ++i) {
+            const int kk = t - i * S;
+            if (kk >= 0 && kk < FS) acc[i] = fmaf(taps.w[kk], x, acc[i]);
+        }
+    }
+    double s = 0.0;
+    unsigned long long z = 0;
+#pragma unroll
+    for (int i = 0; i < FR; ++i) {
+        const int64_t a = a_base + i, b = b0 + i;
+        if (a < a0 + rows_out && b >= 0 && b < m) {
+            D2[(a - a0) * ld2 + b] = acc[i];
+            if (D3 != nullptr) D3[(a - a0) * ld3 + b] = powf(acc[i], p);
+            s += acc[i];
+            z += (acc[i] != 0.f);
+        }
+    }
+    if (sum != nullptr) {
+        s = block_reduce(s, 0.0, OpAdd<double>(), sred);
+        z = block_reduce(z, 0ull, OpAdd<unsigned long long>(), nred);
+        if (threadIdx.x == 0) { atomicAdd(sum, s); atomicAdd(nnz, z); }
+    }
+}
+
+// Any (fs, stride): one output per thread, taps read from the parameter bank with a runtime index.
+__global__ void __launch_bounds__(FT)
+diag_filter_generic_kernel(const float *__restrict__ D1, int64_t ld1, int64_t in_row0, const TapsBig taps,
+                           int fs, int stride, int64_t a0, int64_t rows_out, int64_t m,
+                           float *__restrict__ D2, int64_t ld2, float *__restrict__ D3, int64_t ld3,
+                           float p, double *sum, unsigned long long *nnz) {
+    __shared__ double sred[32];
+    __shared__ unsigned long long nred[32];
+    const int64_t a = a0 + blockIdx.y;
+    const int64_t b = int64_t(blockIdx.x) * FT + threadIdx.x;
+    double s = 0.0;
+    unsigned long long z = 0;
+    if (b < m) {
+        const float *src = D1 + (a * stride - in_row0) * ld1 + b * stride;
+        float acc = 0.f;
+        for (int k = 0; k < fs; ++k) acc = fmaf(taps.w[k], __ldg(src + int64_t(k) * (ld1 + 1)), acc);
+        D2[(a - a0) * ld2 + b] = acc;
+        if (D3 != nullptr) D3[(a - a0) * ld3 + b] = powf(acc, p);
+        s = acc;
+        z = (acc != 0.f);
+    }
+    if (sum != nullptr) {
+        s = block_reduce(s, 0.0, OpAdd<double>(), sred);
+        z = block_reduce(z, 0ull, OpAdd<unsigned long long>(), nred);
+        if (threadIdx.x == 0) { atomicAdd(sum, s); atomicAdd(nnz, z); }
+    }
+}
+
+template <int FS, int S>
+void launch_fast(const float *D1, int64_t ld1, int64_t in_row0, int64_t in_rows, const float *h_w, int64_t a0,
+                 int64_t rows_out, int64_t m, float *D2, int64_t ld2, float *D3, int64_t ld3, float p,
+                 double *sum, unsigned long long *nnz, cudaStream_t st) {
+    Taps64 taps;
+    for (int i = 0; i < 64; ++i) taps.w[i] = (i < FS) ? h_w[i] : 0.f;
+    dim3 grid((unsigned)((m + FR - 1 + FT - 1) / FT), (unsigned)((rows_out + FR - 1) / FR));
+    diag_filter_kernel<FS, S><<<grid, FT, 0, st>>>(D1, ld1, in_row0, in_rows, taps, a0, rows_out, m, D2, ld2, D3,
+                                                   ld3, p, sum, nnz);
+}
+
+}  // namespace
+
+extern "C" int avtex_diag_filter_pow(const float *D1, int64_t ld1, int64_t in_row0, int64_t in_rows, const float *h_w,
+                                     int fs, int stride, int64_t a0, int64_t rows_out, int64_t m,
+                                     float *D2, int64_t ld2, float *D3, int64_t ld3, float p,
+                                     double *sum, unsigned long long *nnz, int device, void *stream) {
+    AVTEX_ENTER(device);
+    AVTEX_REQUIRE(fs >= 1 && fs <= 960 && stride >= 1, "diag_filter: fs=%d stride=%d unsupported", fs, stride);
+    AVTEX_REQUIRE(m >= 1 && rows_out >= 1 && a0 >= 0 && a0 + rows_out <= m && ld2 >= m,
+                  "diag_filter: bad output shape a0=%lld rows=%lld m=%lld", (long long)a0,
+                  (long long)rows_out, (long long)m);
+    AVTEX_REQUIRE(ld1 >= (m - 1) * stride + fs, "diag_filter: ld1=%lld too small", (long long)ld1);
+    AVTEX_REQUIRE(in_row0 >= 0 && in_row0 <= a0 * stride &&
+                      in_row0 + in_rows >= (a0 + rows_out - 1) * stride + fs,
+                  "diag_filter: D1 rows [%lld, %lld) do not cover the rows needed", (long long)in_row0,
+                  (long long)(in_row0 + in_rows));
+    AVTEX_REQUIRE((sum == nullptr) == (nnz == nullptr), "diag_filter: sum and nnz go together");
+    AVTEX_REQUIRE(D3 == nullptr || ld3 >= m, "diag_filter: ld3 too small");
+    cudaStream_t st = as_stream(stream);
+    const int key = fs * 100 + stride;
+#define AVTEX_FAST(FS_, S_)                                                                            \
+    case FS_ * 100 + S_:                                                                               \
+        AVTEX_REQUIRE((rows_out + FR - 1) / FR <= 65535, "diag_filter: too many row bands");           \
+        launch_fast<FS_, S_>(D1, ld1, in_row0, in_rows, h_w, a0, rows_out, m, D2, ld2, D3, ld3, p, sum, nnz, st); \
+        break;
+    switch (key) {
+        AVTEX_FAST(40, 1)
+        AVTEX_FAST(40, 4)
+        AVTEX_FAST(16, 1)
+        AVTEX_FAST(16, 4)
+        AVTEX_FAST(8, 1)
+        default: {
+            AVTEX_REQUIRE(rows_out <= 65535, "diag_filter: generic path limited to 65535 rows per call");
+            TapsBig taps;
+            for (int i = 0; i < 960; ++i) taps.w[i] = (i < fs) ? h_w[i] : 0.f;
+            dim3 grid((unsigned)((m + FT - 1) / FT), (unsigned)rows_out);
+            diag_filter_generic_kernel<<<grid, FT, 0, st>>>(D1, ld1, in_row0, taps, fs, stride, a0, rows_out,
+                                                            m, D2, ld2, D3, ld3, p, sum, nnz);
+        }
+    }
+#undef AVTEX_FAST
+    AVTEX_LAUNCH_CHECK();
+    return 0;
+}

@@ -1,0 +1,144 @@
+// K3 / K4 — future cost ("anticipating the future", classic/q_learning.py:36-51) in vector form.
+//
+// The reference materialises X^{t+1}[i,:] = D3[i,:] + alpha * m^t with m^t_j = min_{k!=j} X^t[j,k] and
+// rebuilds an M x M mask M times per sweep.  Because every row receives the SAME vector, the state
+// of the iteration is the M-vector m alone:
+//     m^{t+1}_j = min_{k != j} ( D3[j,k] + fl(alpha * m^t_k) )  (j >= 1),   m_0 fixed,
+// so one sweep is ONE streaming read of D3 (4 M^2 bytes, HBM-bound; L2-resident when 4 M^2 < ~100 MB).
+// min and a single rounded add are order-free, so every sweep is bit-identical to the reference
+// given the same D3.  The reference's stop test needs eps = mean((X^{t+1}-X^t)^2); its numerator is
+// accumulated (fp64) in the NEXT sweep's read, so no extra pass over D3 is spent on it.
+//
+// fl(alpha*m) and the add are written with __fmul_rn / __fadd_rn: nvcc must not contract them into
+// an FMA, the reference rounds twice (`alpha * mins`, then `D3[i] + ...`).
+#include <float.h>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr int ST = 256;
+
+struct SweepAcc {
+    float mn;
+    double e;
+};
+
+__device__ __forceinline__ void sweep_elem(float v, int64_t k, int64_t j, bool use_a, bool do_eps,
+                                           const float *mp, const float *mp2, float alpha, SweepAcc &acc) {
+    float x = v;
+    if (use_a) x = __fadd_rn(v, __fmul_rn(alpha, mp[k]));
+    if (k != j) acc.mn = fminf(acc.mn, x);
+    if (do_eps) {
+        const float xp = (mp2 != nullptr) ? __fadd_rn(v, __fmul_rn(alpha, mp2[k])) : v;
+        const float d = __fsub_rn(x, xp);
+        acc.e += (double)__fmul_rn(d, d);
+    }
+}
+
+__global__ void __launch_bounds__(ST)
+future_cost_sweep_kernel(const float *__restrict__ D3, int64_t ld, int64_t row0, int64_t m,
+                         const float *__restrict__ mp, const float *__restrict__ mp2, float alpha,
+                         float *__restrict__ m_new, double *eps_sum) {
+    __shared__ float fred[32];
+    __shared__ double dred[32];
+    const int64_t j = row0 + blockIdx.x;
+    const float *row = D3 + int64_t(blockIdx.x) * ld;
+    const bool use_a = (mp != nullptr) && (j >= 1);
+    const bool do_eps = (eps_sum != nullptr) && use_a;
+    SweepAcc acc{FLT_MAX, 0.0};
+    acc.mn = INFINITY;
+    const bool vec = ((reinterpret_cast<uintptr_t>(row) & 15) == 0);
+    const int64_t mv = vec ? (m & ~int64_t(3)) : 0;
+    for (int64_t k = int64_t(threadIdx.x) * 4; k < mv; k += ST * 4) {
+        const float4 v = ld_stream_f4(row + k);
+        sweep_elem(v.x, k + 0, j, use_a, do_eps, mp, mp2, alpha, acc);
+        sweep_elem(v.y, k + 1, j, use_a, do_eps, mp, mp2, alpha, acc);
+        sweep_elem(v.z, k + 2, j, use_a, do_eps, mp, mp2, alpha, acc);
+        sweep_elem(v.w, k + 3, j, use_a, do_eps, mp, mp2, alpha, acc);
+    }
+    for (int64_t k = mv + threadIdx.x; k < m; k += ST)
+        sweep_elem(row[k], k, j, use_a, do_eps, mp, mp2, alpha, acc);
+    const float mn = block_reduce(acc.mn, INFINITY, OpMin(), fred);
+    if (threadIdx.x == 0) m_new[j] = mn;
+    if (do_eps) {
+        const double e = block_reduce(acc.e, 0.0, OpAdd<double>(), dred);
+        if (threadIdx.x == 0) atomicAdd(eps_sum, e);
+    }
+}
+
+__global__ void __launch_bounds__(ST)
+future_cost_finalize_kernel(const float *__restrict__ D3, int64_t ld, int64_t row0, int64_t m,
+                            const float *__restrict__ mvec, float alpha, float *__restrict__ out,
+                            int64_t ld_out, double *sum, unsigned long long *nnz) {
+    __shared__ double sred[32];
+    __shared__ unsigned long long nred[32];
+    const int64_t j = row0 + blockIdx.x;
+    const float *row = D3 + int64_t(blockIdx.x) * ld;
+    float *dst = out + int64_t(blockIdx.x) * ld_out;
+    const bool use_a = (j >= 1);
+    double s = 0.0;
+    unsigned long long z = 0;
+    const bool vec = (((reinterpret_cast<uintptr_t>(row) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0);
+    const int64_t mv = vec ? (m & ~int64_t(3)) : 0;
+    for (int64_t k = int64_t(threadIdx.x) * 4; k < mv; k += ST * 4) {
+        float4 v = ld_stream_f4(row + k);
+        if (use_a) {
+            const float4 a = *reinterpret_cast<const float4 *>(mvec + k);
+            v.x = __fadd_rn(v.x, __fmul_rn(alpha, a.x));
+            v.y = __fadd_rn(v.y, __fmul_rn(alpha, a.y));
+            v.z = __fadd_rn(v.z, __fmul_rn(alpha, a.z));
+            v.w = __fadd_rn(v.w, __fmul_rn(alpha, a.w));
+        }
+        *reinterpret_cast<float4 *>(dst + k) = v;
+        s += (double)v.x + (double)v.y + (double)v.z + (double)v.w;
+        z += (v.x != 0.f) + (v.y != 0.f) + (v.z != 0.f) + (v.w != 0.f);
+    }
+    for (int64_t k = mv + threadIdx.x; k < m; k += ST) {
+        float v = row[k];
+        if (use_a) v = __fadd_rn(v, __fmul_rn(alpha, mvec[k]));
+        dst[k] = v;
+        s += (double)v;
+        z += (v != 0.f);
+    }
+    if (sum != nullptr) {
+        s = block_reduce(s, 0.0, OpAdd<double>(), sred);
+        z = block_reduce(z, 0ull, OpAdd<unsigned long long>(), nred);
+        if (threadIdx.x == 0) { atomicAdd(sum, s); atomicAdd(nnz, z); }
+    }
+}
+
+}  // namespace
+
+extern "C" int avtex_future_cost_sweep(const float *D3, int64_t ld, int64_t row0, int64_t rows, int64_t m,
+                                       const float *m_prev, const float *m_prev2, float alpha,
+                                       float *m_new, double *eps_sum, int device, void *stream) {
+    AVTEX_ENTER(device);
+    AVTEX_REQUIRE(m >= 2 && rows >= 1 && row0 >= 0 && row0 + rows <= m && ld >= m,
+                  "future_cost_sweep: bad shape row0=%lld rows=%lld m=%lld ld=%lld", (long long)row0,
+                  (long long)rows, (long long)m, (long long)ld);
+    AVTEX_REQUIRE(m_prev != nullptr || m_prev2 == nullptr, "future_cost_sweep: m_prev2 without m_prev");
+    AVTEX_REQUIRE(((reinterpret_cast<uintptr_t>(m_prev) | reinterpret_cast<uintptr_t>(m_prev2)) & 15) == 0,
+                  "future_cost_sweep: m vectors must be 16-byte aligned");
+    future_cost_sweep_kernel<<<(unsigned)rows, ST, 0, as_stream(stream)>>>(D3, ld, row0, m, m_prev, m_prev2,
+                                                                           alpha, m_new, eps_sum);
+    AVTEX_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int avtex_future_cost_finalize(const float *D3, int64_t ld, int64_t row0, int64_t rows,
+                                          int64_t m, const float *mvec, float alpha, float *D3_new,
+                                          int64_t ld_out, double *sum, unsigned long long *nnz,
+                                          int device, void *stream) {
+    AVTEX_ENTER(device);
+    AVTEX_REQUIRE(m >= 1 && rows >= 1 && row0 >= 0 && row0 + rows <= m && ld >= m && ld_out >= m,
+                  "future_cost_finalize: bad shape row0=%lld rows=%lld m=%lld", (long long)row0,
+                  (long long)rows, (long long)m);
+    AVTEX_REQUIRE(mvec != nullptr && (reinterpret_cast<uintptr_t>(mvec) & 15) == 0,
+                  "future_cost_finalize: mvec must be non-NULL and 16-byte aligned");
+    AVTEX_REQUIRE((sum == nullptr) == (nnz == nullptr), "future_cost_finalize: sum and nnz go together");
+    future_cost_finalize_kernel<<<(unsigned)rows, ST, 0, as_stream(stream)>>>(D3, ld, row0, m, mvec, alpha,
+                                                                              D3_new, ld_out, sum, nnz);
+    AVTEX_LAUNCH_CHECK();
+    return 0;
+}

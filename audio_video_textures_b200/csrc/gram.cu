@@ -1,0 +1,428 @@
+// K1 — pairwise frame L2 distances as a Gram contraction on the 5th-gen tensor cores.
+//
+//   D[r,c] = sqrt( n_r + n_c - 2 <x_r, x_c> )        replaces classic/computeD1.py:50-56, 58-96
+//
+// x are the centred signed-byte frames written by K0 (pack.cu), n their exact squared norms.
+// tcgen05.mma kind::i8 (s8 x s8 -> s32 accumulated in TMEM) makes <x_r, x_c> an exact integer, so
+// d^2 is exact: no cancellation error, duplicate frames give exactly 0 (the reference's sigma
+// counts `nonzero(D1)`), and the only rounding left is one fp32 sqrt.  d^2 is evaluated modulo 2^32
+// in the epilogue, which is exact whenever the true d^2 < 2^32; the host wrapper guarantees that
+// through (sqrt(n_r)+sqrt(n_c))^2 <= 4 max(n) < 2^32 and otherwise routes to direct.cu.
+//
+// Structure (one persistent CTA per SM, 6 warps, warp-specialised):
+//   warp 0      TMA producer: cp.async.bulk.tensor 128B-swizzled tiles A[128 x 128B], B[256 x 128B]
+//               into a 4-stage shared-memory ring, completion on mbarriers.
+//   warp 1      MMA issuer (one lane): 4 x tcgen05.mma (M128 N256 K32) per stage, accumulators
+//               double-buffered in TMEM (2 x 256 columns); tcgen05.commit releases stages / signals
+//               the epilogue.
+//   warps 2-5   epilogue: tcgen05.ld 32 lanes x 32 columns at a time, fused  n_r + n_c - 2g -> sqrt,
+//               direct + mirrored stores, fused fp64 sum / non-zero count for sigma.
+//   Tiles are visited in groups of 8 row-tiles so one wave's operand footprint stays inside L2;
+//   in symmetric mode only tiles touching the upper triangle are computed (~half the MMAs).
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr int BM = 128;                 // tile rows  (UMMA M)
+constexpr int BN = 256;                 // tile cols  (UMMA N)
+constexpr int BKB = 128;                // K bytes per stage = one 128B swizzle atom
+constexpr int UMMA_KB = 32;             // K bytes per tcgen05.mma (kind::i8: K = 32)
+constexpr int STAGES = 4;
+constexpr int A_BYTES = BM * BKB;       // 16 KB
+constexpr int B_BYTES = BN * BKB;       // 32 KB
+constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+constexpr int GROUP_M = 8;
+constexpr int NUM_THREADS = 192;
+constexpr int TMEM_COLS = 512;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+
+// kind::i8 instruction descriptor (cute/arch/mma_sm100_desc.hpp bit layout):
+//   c_format[4,6)=2 (S32) | a_format[7,10)=1 (s8) | b_format[10,13)=1 (s8) | a/b major = K (0)
+//   n_dim[17,23) = N>>3 | m_dim[24,29) = M>>4
+constexpr uint32_t IDESC_S8 = (2u << 4) | (1u << 7) | (1u << 10) | (uint32_t(BN >> 3) << 17) |
+                              (uint32_t(BM >> 4) << 24);
+
+struct GramArgs {
+    int64_t n, kp, row0, rows, ldd;
+    const int64_t *sqnorm;
+    float *D;
+    double *sum;
+    unsigned long long *nnz;
+    int symmetric, TM, TN, num_tiles;
+};
+
+// ------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+// Bounded wait: a protocol bug must surface as a trapped kernel, never as a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > 8000000000LL) {
+            printf("avtex gram: mbarrier timeout (block %d thread %d bar %u parity %u)\n", blockIdx.x,
+                   threadIdx.x, bar, parity);
+            __trap();
+        }
+    }
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols));
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void umma_s8(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                        uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+// K-major, 128B-swizzled operand tile: rows are 128 B, 8-row groups are 1024 B apart (SBO),
+// LBO is ignored for swizzled K-major layouts (set to 1), descriptor version 1 (Blackwell).
+__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= uint64_t((smem_addr & 0x3FFFFu) >> 4);
+    d |= uint64_t(1) << 16;
+    d |= uint64_t(1024 >> 4) << 32;
+    d |= uint64_t(1) << 46;
+    d |= uint64_t(2) << 61;
+    return d;
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// ------------------------------------------------------------------ tile schedule
+// Row-tiles are taken in groups of GROUP_M; inside a group the order is column-major, so a wave of
+// CTAs shares <= GROUP_M A-tiles and ~148/GROUP_M B-tiles (L2 footprint instead of DRAM streaming).
+// Symmetric mode keeps tile (tm, tn) iff it intersects the upper triangle: tn >= tm / 2.
+__host__ __device__ inline int sym_group_count(int g, int TM, int TN, int *gm_out) {
+    const int first = g * GROUP_M;
+    const int gm = (TM - first < GROUP_M) ? (TM - first) : GROUP_M;
+    const int tn0 = first / 2;
+    int cnt = 0;
+    for (int j = 0; j < GROUP_M / 2; ++j)
+        if (tn0 + j < TN) cnt += (gm < 2 * j + 2) ? gm : (2 * j + 2);
+    const int full = TN - (tn0 + GROUP_M / 2);
+    if (full > 0) cnt += full * gm;
+    *gm_out = gm;
+    return cnt;
+}
+
+__host__ __device__ inline void decode_tile(int t, int TM, int TN, int symmetric, int *tm, int *tn) {
+    if (!symmetric) {
+        const int per_group = GROUP_M * TN;
+        const int g = t / per_group;
+        const int first = g * GROUP_M;
+        const int gm = (TM - first < GROUP_M) ? (TM - first) : GROUP_M;
+        const int rem = t - g * per_group;
+        *tn = rem / gm;
+        *tm = first + rem % gm;
+        return;
+    }
+    for (int g = 0;; ++g) {
+        int gm;
+        const int cnt = sym_group_count(g, TM, TN, &gm);
+        if (t < cnt) {
+            const int first = g * GROUP_M, tn0 = first / 2;
+            for (int j = 0; j < GROUP_M / 2; ++j) {
+                if (tn0 + j >= TN) break;
+                const int c = (gm < 2 * j + 2) ? gm : (2 * j + 2);
+                if (t < c) { *tm = first + t; *tn = tn0 + j; return; }
+                t -= c;
+            }
+            *tm = first + t % gm;
+            *tn = tn0 + GROUP_M / 2 + t / gm;
+            return;
+        }
+        t -= cnt;
+    }
+}
+
+int count_tiles(int TM, int TN, int symmetric) {
+    if (!symmetric) return TM * TN;
+    int total = 0, gm;
+    for (int g = 0; g * GROUP_M < TM; ++g) total += sym_group_count(g, TM, TN, &gm);
+    return total;
+}
+
+// ------------------------------------------------------------------ kernel
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gram_l2_s8_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                  const GramArgs args) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t tiles = (raw + 1023u) & ~1023u;                     // SWIZZLE_128B needs 1024 B alignment
+    const uint32_t bars = tiles + STAGES * STAGE_BYTES;
+    const uint32_t full_bar = bars, empty_bar = bars + 8 * STAGES;
+    const uint32_t tfull_bar = bars + 16 * STAGES, tempty_bar = tfull_bar + 16;
+    const uint32_t tmem_slot = tempty_bar + 16;
+    uint32_t *tmem_slot_ptr = reinterpret_cast<uint32_t *>(smem_raw + (tmem_slot - raw));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int KB = int(args.kp / BKB);
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
+        for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar + 8 * s, 1); mbar_init(empty_bar + 8 * s, 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar + 8 * s, 1); mbar_init(tempty_bar + 8 * s, 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int t = blockIdx.x; t < args.num_tiles; t += gridDim.x) {
+                int tm, tn;
+                decode_tile(t, args.TM, args.TN, args.symmetric, &tm, &tn);
+                const int row_a = int(args.row0) + tm * BM, row_b = tn * BN;
+                for (int kb = 0; kb < KB; ++kb) {
+                    mbar_wait(empty_bar + 8 * stage, phase ^ 1);
+                    const uint32_t sa = tiles + stage * STAGE_BYTES, sb = sa + A_BYTES;
+                    mbar_arrive_expect_tx(full_bar + 8 * stage, STAGE_BYTES);
+                    tma_load_2d(sa, &map_a, full_bar + 8 * stage, kb * BKB, row_a);
+                    tma_load_2d(sb, &map_b, full_bar + 8 * stage, kb * BKB, row_b);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            int stage = 0, acc = 0;
+            uint32_t phase = 0, acc_phase = 0;
+            for (int t = blockIdx.x; t < args.num_tiles; t += gridDim.x) {
+                mbar_wait(tempty_bar + 8 * acc, acc_phase ^ 1);          // epilogue drained this TMEM buffer
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + uint32_t(acc * BN);
+                for (int kb = 0; kb < KB; ++kb) {
+                    mbar_wait(full_bar + 8 * stage, phase);               // TMA bytes have landed
+                    tc_fence_after();
+                    const uint32_t sa = tiles + stage * STAGE_BYTES, sb = sa + A_BYTES;
+                    const uint64_t da = make_desc_sw128(sa), db = make_desc_sw128(sb);
+#pragma unroll
+                    for (int k = 0; k < BKB / UMMA_KB; ++k)
+                        umma_s8(d_tmem, da + uint64_t(k * (UMMA_KB >> 4)), db + uint64_t(k * (UMMA_KB >> 4)),
+                                IDESC_S8, (kb | k) != 0);
+                    umma_commit(empty_bar + 8 * stage);                   // frees the smem stage when the MMAs retire
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+                umma_commit(tfull_bar + 8 * acc);                         // accumulator complete -> epilogue
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else {
+        // ===================== epilogue (warps 2..5) =====================
+        const int quarter = warp & 3;                                     // TMEM lane quarter this warp may read
+        const int row_in_tile = quarter * 32 + lane;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        double s_acc = 0.0;
+        unsigned long long z_acc = 0;
+        const int64_t row_end = args.row0 + args.rows;
+        for (int t = blockIdx.x; t < args.num_tiles; t += gridDim.x) {
+            int tm, tn;
+            decode_tile(t, args.TM, args.TN, args.symmetric, &tm, &tn);
+            const int64_t r = args.row0 + int64_t(tm) * BM + row_in_tile;
+            const int64_t c0 = int64_t(tn) * BN;
+            const bool r_ok = r < row_end;
+            const uint32_t nr = r_ok ? (uint32_t)__ldg(args.sqnorm + r) : 0u;
+            float *drow = args.D + (r - args.row0) * args.ldd;
+            const bool vec_ok = ((reinterpret_cast<uintptr_t>(drow) & 15) == 0);
+            mbar_wait(tfull_bar + 8 * acc, acc_phase);
+            tc_fence_after();
+            const uint32_t t_base = tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(acc * BN);
+#pragma unroll 1
+            for (int cc = 0; cc < BN / 32; ++cc) {
+                uint32_t g[32];
+                tmem_ld32(t_base + cc * 32, g);
+                if (cc == BN / 32 - 1) {                                  // all of this warp's reads are done
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(tempty_bar + 8 * acc);
+                }
+                const int64_t cbase = c0 + cc * 32;
+                if (cbase >= args.n) continue;
+                if (args.symmetric && cbase + 31 < args.row0 + int64_t(tm) * BM + quarter * 32) continue;  // whole chunk below diagonal for this warp
+                float d[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const int64_t c = cbase + j;
+                    const uint32_t nc = (c < args.n) ? (uint32_t)__ldg(args.sqnorm + c) : 0u;
+                    const uint32_t d2 = nr + nc - 2u * g[j];              // exact mod 2^32
+                    d[j] = __fsqrt_rn(__uint2float_rn(d2));
+                }
+                if (!args.symmetric) {
+                    if (r_ok) {
+                        if (vec_ok && cbase + 32 <= args.n) {
+#pragma unroll
+                            for (int j = 0; j < 32; j += 4)
+                                *reinterpret_cast<float4 *>(drow + cbase + j) = make_float4(d[j], d[j + 1], d[j + 2], d[j + 3]);
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) { s_acc += (double)d[j]; z_acc += (d[j] != 0.f); }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j)
+                                if (cbase + j < args.n) { drow[cbase + j] = d[j]; s_acc += (double)d[j]; z_acc += (d[j] != 0.f); }
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const int64_t c = cbase + j;
+                        if (r_ok && c < args.n && r <= c) {
+                            drow[c] = d[j];
+                            if (r < c) {
+                                args.D[c * args.ldd + r] = d[j];          // mirrored store: coalesced across the warp
+                                s_acc += 2.0 * (double)d[j];
+                                z_acc += 2ull * (d[j] != 0.f);
+                            }
+                        }
+                    }
+                }
+            }
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+        if (args.sum != nullptr) {
+            s_acc = warp_sum(s_acc);
+            z_acc = warp_sum(z_acc);
+            if (lane == 0) { atomicAdd(args.sum, s_acc); atomicAdd(args.nnz, z_acc); }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+// ------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+
+int get_encode_fn(EncodeTiledFn *out) {
+    static EncodeTiledFn cached = nullptr;
+    if (cached == nullptr) {
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        AVTEX_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+        AVTEX_REQUIRE(fn != nullptr && qres == cudaDriverEntryPointSuccess,
+                      "cuTensorMapEncodeTiled not available from the driver");
+        cached = reinterpret_cast<EncodeTiledFn>(fn);
+    }
+    *out = cached;
+    return 0;
+}
+
+int make_map(EncodeTiledFn enc, CUtensorMap *map, const void *base, int64_t n, int64_t kp, int box_rows) {
+    const cuuint64_t gdim[2] = {(cuuint64_t)kp, (cuuint64_t)n};
+    const cuuint64_t gstride[1] = {(cuuint64_t)kp};
+    const cuuint32_t box[2] = {(cuuint32_t)BKB, (cuuint32_t)box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void *>(base), gdim, gstride, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    AVTEX_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+    return 0;
+}
+
+}  // namespace
+
+extern "C" int avtex_gram_l2_s8(const int8_t *packed, int64_t n, int64_t kp, const int64_t *sqnorm,
+                                int64_t row0, int64_t rows, int symmetric, float *D, int64_t ldd,
+                                double *sum, unsigned long long *nnz, int device, void *stream) {
+    AVTEX_ENTER(device);
+    AVTEX_REQUIRE(n >= 1 && n < (int64_t(1) << 30) && kp >= BKB && kp % BKB == 0 && kp < (int64_t(1) << 31),
+                  "gram_l2_s8: bad shape n=%lld kp=%lld", (long long)n, (long long)kp);
+    AVTEX_REQUIRE(rows >= 1 && row0 >= 0 && row0 + rows <= n && ldd >= n, "gram_l2_s8: bad row block [%lld,+%lld)",
+                  (long long)row0, (long long)rows);
+    AVTEX_REQUIRE(!symmetric || (row0 == 0 && rows == n), "gram_l2_s8: symmetric mode needs the full matrix");
+    AVTEX_REQUIRE((reinterpret_cast<uintptr_t>(packed) & 127) == 0, "gram_l2_s8: packed must be 128-byte aligned");
+    AVTEX_REQUIRE((sum == nullptr) == (nnz == nullptr), "gram_l2_s8: sum and nnz go together");
+    int cc = 0, sms = 0;
+    if (int rc = avtex_device_info(device, &sms, &cc)) return rc;
+    AVTEX_REQUIRE(cc == 100, "gram_l2_s8: needs an sm_100 device (tcgen05 kind::i8), got cc %d", cc);
+
+    EncodeTiledFn enc;
+    if (int rc = get_encode_fn(&enc)) return rc;
+    CUtensorMap map_a, map_b;
+    if (int rc = make_map(enc, &map_a, packed, n, kp, BM)) return rc;
+    if (int rc = make_map(enc, &map_b, packed, n, kp, BN)) return rc;
+
+    GramArgs a;
+    a.n = n; a.kp = kp; a.row0 = row0; a.rows = rows; a.ldd = ldd;
+    a.sqnorm = sqnorm; a.D = D; a.sum = sum; a.nnz = nnz;
+    a.symmetric = symmetric ? 1 : 0;
+    a.TM = int((rows + BM - 1) / BM);
+    a.TN = int((n + BN - 1) / BN);
+    a.num_tiles = count_tiles(a.TM, a.TN, a.symmetric);
+    static bool attr_set[64] = {false};
+    if (device < 64 && !attr_set[device]) {
+        AVTEX_CUDA(cudaFuncSetAttribute(gram_l2_s8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        attr_set[device] = true;
+    }
+    const int grid = a.num_tiles < sms ? a.num_tiles : sms;
+    gram_l2_s8_kernel<<<grid, NUM_THREADS, SMEM_BYTES, as_stream(stream)>>>(map_a, map_b, a);
+    AVTEX_LAUNCH_CHECK();
+    return 0;
+}
+
+// Exposed for tests: the tile schedule must cover every needed tile exactly once.
+extern "C" int avtex_gram_tile_schedule(int TM, int TN, int symmetric, int *tm_out, int *tn_out, int capacity) {
+    const int total = count_tiles(TM, TN, symmetric);
+    if (tm_out == nullptr) return total;
+    for (int t = 0; t < total && t < capacity; ++t) decode_tile(t, TM, TN, symmetric, &tm_out[t], &tn_out[t]);
+    return total;
+}

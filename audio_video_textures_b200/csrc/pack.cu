@@ -1,0 +1,118 @@
+// K0 — frame packing: [n,k] u8 / integer-valued f32  ->  centred s8 [n,kp] + exact squared norms.
+// HBM-bound: reads n*k*(1|4) B, writes n*kp B + 8n B.  One CTA per frame row, 128-bit accesses.
+#include "common.cuh"
+
+namespace {
+
+constexpr int PACK_THREADS = 256;
+
+// 16 centred bytes from 16 raw u8: x - 128 == x ^ 0x80 reinterpreted as s8.
+__device__ __forceinline__ uint4 centre16(uint4 v) {
+    v.x ^= 0x80808080u; v.y ^= 0x80808080u; v.z ^= 0x80808080u; v.w ^= 0x80808080u;
+    return v;
+}
+
+__device__ __forceinline__ int sq4(unsigned int w) {            // sum of squares of 4 packed s8
+    return __dp4a((int)w, (int)w, 0);
+}
+
+__global__ void __launch_bounds__(PACK_THREADS)
+pack_u8_kernel(const uint8_t *__restrict__ in, int64_t k, int64_t ld, int8_t *__restrict__ out,
+               int64_t kp, int64_t *__restrict__ sqnorm) {
+    __shared__ unsigned long long scratch[32];
+    const int64_t row = blockIdx.x;
+    const uint8_t *src = in + row * ld;
+    int8_t *dst = out + row * kp;
+    unsigned long long acc = 0;
+    const bool vec = ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
+    const int64_t kv = vec ? (k & ~int64_t(15)) : 0;
+    for (int64_t c = int64_t(threadIdx.x) * 16; c < kv; c += int64_t(PACK_THREADS) * 16) {
+        uint4 v = centre16(*reinterpret_cast<const uint4 *>(src + c));
+        acc += (unsigned)(sq4(v.x) + sq4(v.y) + sq4(v.z) + sq4(v.w));   // <= 16*16384
+        *reinterpret_cast<uint4 *>(dst + c) = v;
+    }
+    for (int64_t c = kv + threadIdx.x; c < kp; c += PACK_THREADS) {
+        int v = (c < k) ? int(src[c]) - 128 : 0;
+        acc += (unsigned)(v * v);
+        dst[c] = (int8_t)v;
+    }
+    acc = block_reduce(acc, 0ull, OpAdd<unsigned long long>(), scratch);
+    if (threadIdx.x == 0) sqnorm[row] = (int64_t)acc;
+}
+
+__global__ void __launch_bounds__(PACK_THREADS)
+pack_f32_kernel(const float *__restrict__ in, int64_t k, int64_t ld, int8_t *__restrict__ out,
+                int64_t kp, int64_t *__restrict__ sqnorm, int *__restrict__ flags) {
+    __shared__ unsigned long long scratch[32];
+    const int64_t row = blockIdx.x;
+    const float *src = in + row * ld;
+    int8_t *dst = out + row * kp;
+    unsigned long long acc = 0;
+    int bad = 0;
+    const bool vec = ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
+    const int64_t kv = vec ? (k & ~int64_t(15)) : 0;
+    for (int64_t c = int64_t(threadIdx.x) * 16; c < kv; c += int64_t(PACK_THREADS) * 16) {
+        unsigned int w[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            float4 f = ld_stream_f4(src + c + 4 * q);
+            float e[4] = {f.x, f.y, f.z, f.w};
+            unsigned int pk = 0;
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                float r = rintf(e[b]);
+                bad |= !(r == e[b] && r >= 0.f && r <= 255.f);
+                int v = (int)r - 128;
+                acc += (unsigned)(v * v);
+                pk |= (unsigned)(v & 0xff) << (8 * b);
+            }
+            w[q] = pk;
+        }
+        *reinterpret_cast<uint4 *>(dst + c) = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+    for (int64_t c = kv + threadIdx.x; c < kp; c += PACK_THREADS) {
+        int v = 0;
+        if (c < k) {
+            float e = src[c], r = rintf(e);
+            bad |= !(r == e && r >= 0.f && r <= 255.f);
+            v = (int)r - 128;
+        }
+        acc += (unsigned)(v * v);
+        dst[c] = (int8_t)v;
+    }
+    acc = block_reduce(acc, 0ull, OpAdd<unsigned long long>(), scratch);
+    if (threadIdx.x == 0) sqnorm[row] = (int64_t)acc;
+    if (__syncthreads_or(bad) && threadIdx.x == 0) atomicOr(flags, 1);
+}
+
+}  // namespace
+
+static int check_pack(int64_t n, int64_t k, int64_t ld, int64_t kp) {
+    AVTEX_REQUIRE(n > 0 && k > 0 && ld >= k, "pack_frames: bad shape n=%lld k=%lld ld=%lld",
+                  (long long)n, (long long)k, (long long)ld);
+    AVTEX_REQUIRE(kp >= k && kp % 128 == 0, "pack_frames: kp=%lld must be >= k and a multiple of 128",
+                  (long long)kp);
+    AVTEX_REQUIRE(n < (int64_t(1) << 31), "pack_frames: n too large");
+    return 0;
+}
+
+extern "C" int avtex_pack_frames_u8(const uint8_t *frames, int64_t n, int64_t k, int64_t ld,
+                                    int8_t *packed, int64_t kp, int64_t *sqnorm, int device,
+                                    void *stream) {
+    AVTEX_ENTER(device);
+    if (int rc = check_pack(n, k, ld, kp)) return rc;
+    pack_u8_kernel<<<(unsigned)n, PACK_THREADS, 0, as_stream(stream)>>>(frames, k, ld, packed, kp, sqnorm);
+    AVTEX_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int avtex_pack_frames_f32(const float *frames, int64_t n, int64_t k, int64_t ld,
+                                     int8_t *packed, int64_t kp, int64_t *sqnorm, int *flags,
+                                     int device, void *stream) {
+    AVTEX_ENTER(device);
+    if (int rc = check_pack(n, k, ld, kp)) return rc;
+    AVTEX_REQUIRE(flags != nullptr, "pack_frames_f32: flags must not be NULL");
+    pack_f32_kernel<<<(unsigned)n, PACK_THREADS, 0, as_stream(stream)>>>(frames, k, ld, packed, kp, sqnorm, flags);
+    AVTEX_LAUNCH_CHECK();
+    return 0;
+}

@@ -1,0 +1,322 @@
+"""Host-side engine: thin, allocation-explicit wrappers over the C ABI (include/avtex.h).
+
+Everything here takes / returns CUDA tensors and launches on the current torch stream; torch is
+used for device memory and streams only.  Row-range arguments (`row0`, `rows`, `a0`, ...) exist so
+the same calls serve the row-sharded multi-GPU path (dist.py).  No function here falls back to
+PyTorch arithmetic: a missing library or a failed kernel raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+
+import numpy as np
+import torch
+
+from . import _lib
+
+F32_EPS_STOP = 10e-3            # classic/q_learning.py:39  `while eps > 10e-3`
+
+
+def _dev(t: torch.Tensor) -> int:
+    if not t.is_cuda:
+        raise ValueError("expected a CUDA tensor")
+    return t.device.index if t.device.index is not None else torch.cuda.current_device()
+
+
+def _stream(t: torch.Tensor):
+    return C.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+
+
+def _f32(x) -> np.float32:
+    """Python float / 0-dim tensor -> fp32 exactly as an ATen scalar operand is cast."""
+    if isinstance(x, torch.Tensor):
+        return np.float32(x.detach().cpu().item())
+    return np.float32(x)
+
+
+# --------------------------------------------------------------------------- stats / sigma
+def new_stats(device) -> torch.Tensor:
+    """16-byte accumulator: [fp64 sum | uint64 nnz]."""
+    return torch.zeros(2, dtype=torch.float64, device=device)
+
+
+def _stats_ptrs(stats):
+    if stats is None:
+        return None, None
+    base = stats.data_ptr()
+    return C.c_void_p(base), C.c_void_p(base + 8)
+
+
+def read_stats(stats: torch.Tensor):
+    """(sum: float, nnz: int) — one D2H copy + sync."""
+    h = stats.cpu()
+    return float(h[0]), int(h.view(torch.int64)[1])
+
+
+def sigma_from_stats(total: float, nnz: int, sigma_factor) -> np.float32:
+    """sigma = f * (sum(D) / nnz) in fp32 (classic/computeD1.py:240-241): the fp32 sum divided by
+    the count cast to fp32, then multiplied by fp32(f)."""
+    return _f32(sigma_factor) * (np.float32(total) / np.float32(nnz))
+
+
+def sum_nnz(D: torch.Tensor, stats: torch.Tensor | None = None) -> torch.Tensor:
+    stats = new_stats(D.device) if stats is None else stats
+    s, z = _stats_ptrs(stats)
+    _lib.call("avtex_sum_nnz", _lib.ptr(D), D.shape[0], D.shape[1], D.stride(0), s, z, _dev(D), _stream(D))
+    return stats
+
+
+# --------------------------------------------------------------------------- K0 / K1
+@dataclass
+class PackedFrames:
+    packed: torch.Tensor          # [N, Kp] int8, centred
+    sqnorm: torch.Tensor          # [N] int64
+    k: int
+    exact_ok: bool                # False -> use the direct path
+    reason: str = ""
+
+
+GRAM_MAX_SQNORM = (1 << 32) // 4  # (sqrt(n_r)+sqrt(n_c))^2 <= 4 max(n) must stay below 2^32
+
+
+def pack_frames(frames: torch.Tensor) -> PackedFrames:
+    """K0.  frames: CUDA tensor [N, ...] uint8 or float (integer-valued 0..255)."""
+    x = frames.reshape(frames.shape[0], -1)
+    if x.stride(-1) != 1:
+        x = x.contiguous()
+    n, k = x.shape
+    kp = (k + 127) // 128 * 128
+    packed = torch.empty((n, kp), dtype=torch.int8, device=x.device)
+    sqnorm = torch.empty(n, dtype=torch.int64, device=x.device)
+    dev, st = _dev(x), _stream(x)
+    ok, reason = True, ""
+    if x.dtype == torch.uint8:
+        _lib.call("avtex_pack_frames_u8", _lib.ptr(x), n, k, x.stride(0), _lib.ptr(packed), kp,
+                  _lib.ptr(sqnorm), dev, st)
+    elif x.dtype == torch.float32:
+        flags = torch.zeros(1, dtype=torch.int32, device=x.device)
+        _lib.call("avtex_pack_frames_f32", _lib.ptr(x), n, k, x.stride(0), _lib.ptr(packed), kp,
+                  _lib.ptr(sqnorm), _lib.ptr(flags), dev, st)
+        if int(flags.item()) != 0:
+            ok, reason = False, "frames are not integer-valued bytes"
+    else:
+        raise TypeError(f"frames dtype {x.dtype} not supported (uint8 or float32)")
+    if ok and kp * 128 * 128 >= GRAM_MAX_SQNORM:           # only then can a norm exceed the bound
+        if int(sqnorm.max().item()) >= GRAM_MAX_SQNORM:
+            ok, reason = False, "squared norms too large for the mod-2^32 epilogue"
+    return PackedFrames(packed, sqnorm, k, ok, reason)
+
+
+def gram_l2(pf: PackedFrames, row0: int = 0, rows: int | None = None, symmetric: bool | None = None,
+            stats: torch.Tensor | None = None, out: torch.Tensor | None = None) -> torch.Tensor:
+    """K1 on tensor cores.  Returns D[rows, N] for global rows [row0, row0+rows)."""
+    n, kp = pf.packed.shape
+    rows = n - row0 if rows is None else rows
+    if symmetric is None:
+        symmetric = (row0 == 0 and rows == n)
+    D = torch.empty((rows, n), dtype=torch.float32, device=pf.packed.device) if out is None else out
+    s, z = _stats_ptrs(stats)
+    _lib.call("avtex_gram_l2_s8", _lib.ptr(pf.packed), n, kp, _lib.ptr(pf.sqnorm), row0, rows,
+              1 if symmetric else 0, _lib.ptr(D), D.stride(0), s, z, _dev(D), _stream(D))
+    return D
+
+
+def pairdist_direct(frames: torch.Tensor, row0: int = 0, rows: int | None = None,
+                    stats: torch.Tensor | None = None) -> torch.Tensor:
+    """K1 fallback: direct difference in fp32 (any float features, or uint8)."""
+    x = frames.reshape(frames.shape[0], -1)
+    if x.stride(-1) != 1:
+        x = x.contiguous()
+    n, k = x.shape
+    rows = n - row0 if rows is None else rows
+    D = torch.empty((rows, n), dtype=torch.float32, device=x.device)
+    s, z = _stats_ptrs(stats)
+    name = {torch.float32: "avtex_pairdist_direct_f32", torch.uint8: "avtex_pairdist_direct_u8"}.get(x.dtype)
+    if name is None:
+        raise TypeError(f"frames dtype {x.dtype} not supported (uint8 or float32)")
+    _lib.call(name, _lib.ptr(x), n, k, x.stride(0), row0, rows, _lib.ptr(D), D.stride(0), s, z, _dev(D), _stream(D))
+    return D
+
+
+def pairwise_l2(frames: torch.Tensor, row0: int = 0, rows: int | None = None,
+                stats: torch.Tensor | None = None, method: str = "auto"):
+    """D1 rows [row0, row0+rows).  method: auto | gram | direct.  Returns (D, method_used)."""
+    if method not in ("auto", "gram", "direct"):
+        raise ValueError(method)
+    if method != "direct" and frames.dtype in (torch.uint8, torch.float32):
+        pf = pack_frames(frames)
+        if pf.exact_ok:
+            return gram_l2(pf, row0, rows, stats=stats), "gram"
+        if method == "gram":
+            raise _lib.AvtexError(f"gram path not applicable: {pf.reason}")
+    return pairdist_direct(frames if frames.dtype == torch.uint8 else frames.float(), row0, rows, stats), "direct"
+
+
+# --------------------------------------------------------------------------- K5
+def transition_probs(D: torch.Tensor, sigma, shift: int = 1, rows_out: int | None = None,
+                     threshold: float | None = None, want_P: bool = True, want_counts: bool = False):
+    """P (and thresholded P_new) for output rows [0, rows_out) from source rows min(i+shift, rows-1)."""
+    rows_in, cols = D.shape
+    rows_out = rows_in if rows_out is None else rows_out
+    P = torch.empty((rows_out, cols), dtype=torch.float32, device=D.device) if want_P else None
+    Pn = torch.empty((rows_out, cols), dtype=torch.float32, device=D.device) if threshold is not None else None
+    counts = torch.empty(rows_out, dtype=torch.int32, device=D.device) if want_counts else None
+    th = _f32(threshold) if threshold is not None else np.float32(-1.0)
+    _lib.call("avtex_transition_probs", _lib.ptr(D), D.stride(0), rows_in, cols, C.c_float(_f32(sigma)), shift,
+              rows_out, _lib.ptr(P), cols, C.c_float(th), _lib.ptr(Pn), cols, _lib.ptr(counts), _dev(D), _stream(D))
+    return P, Pn, counts
+
+
+def csr_from_matrix(P: torch.Tensor, counts: torch.Tensor | None = None):
+    """Ascending non-zero columns per row -> (rowptr int64 numpy, colidx int32 numpy).  One sync."""
+    rows, cols = P.shape
+    if counts is None:
+        counts = torch.empty(rows, dtype=torch.int32, device=P.device)
+        _lib.call("avtex_row_nnz", _lib.ptr(P), P.stride(0), rows, cols, _lib.ptr(counts), _dev(P), _stream(P))
+    rowptr = torch.zeros(rows + 1, dtype=torch.int64, device=P.device)
+    torch.cumsum(counts, 0, out=rowptr[1:])
+    total = int(rowptr[-1].item())
+    colidx = torch.empty(max(total, 1), dtype=torch.int32, device=P.device)
+    _lib.call("avtex_csr_fill", _lib.ptr(P), P.stride(0), rows, cols, _lib.ptr(rowptr), _lib.ptr(colidx),
+              _dev(P), _stream(P))
+    return rowptr.cpu().numpy(), colidx[:total].cpu().numpy()
+
+
+# --------------------------------------------------------------------------- K2
+def binomial_taps(filter_size: int) -> np.ndarray:
+    """classic/computeD2.py:34 — coeffs((0.5 x + 0.5)^(fs-1)) evaluated in float64, cast to fp32."""
+    return np.asarray((np.poly1d([0.5, 0.5]) ** (filter_size - 1)).coeffs, dtype=np.float32).reshape(-1)
+
+
+def filtered_size(n: int, filter_size: int, stride: int) -> int:
+    return (n - filter_size) // stride + 1
+
+
+def diag_filter(D1: torch.Tensor, filter_size: int, stride: int = 1, p: float | None = None,
+                m: int | None = None, a0: int = 0, rows_out: int | None = None, in_row0: int = 0,
+                stats: torch.Tensor | None = None, taps: np.ndarray | None = None):
+    """K2.  D1 holds global rows [in_row0, in_row0 + D1.shape[0]) and all columns.
+    Returns (D2[rows_out, m], D3 | None)."""
+    n_cols = D1.shape[1]
+    m = filtered_size(n_cols, filter_size, stride) if m is None else m
+    rows_out = m - a0 if rows_out is None else rows_out
+    taps = binomial_taps(filter_size) if taps is None else np.ascontiguousarray(taps, dtype=np.float32)
+    if taps.shape[0] != filter_size:
+        raise ValueError("taps length != filter_size")
+    D2 = torch.empty((rows_out, m), dtype=torch.float32, device=D1.device)
+    D3 = torch.empty((rows_out, m), dtype=torch.float32, device=D1.device) if p is not None else None
+    s, z = _stats_ptrs(stats)
+    _lib.call("avtex_diag_filter_pow", _lib.ptr(D1), D1.stride(0), in_row0, D1.shape[0],
+              taps.ctypes.data_as(C.POINTER(C.c_float)), filter_size, stride, a0, rows_out, m,
+              _lib.ptr(D2), m, _lib.ptr(D3), m, C.c_float(_f32(p if p is not None else 1.0)), s, z,
+              _dev(D1), _stream(D1))
+    return D2, D3
+
+
+# --------------------------------------------------------------------------- K3 / K4
+@dataclass
+class FutureCostResult:
+    mvec: torch.Tensor            # [M (padded)] fp32: D3_new = D3 + fl(alpha*mvec) on rows >= 1
+    n_sweeps: int                 # == number of `Eps:` lines the reference prints
+    eps_trail: list = field(default_factory=list)
+    passes: int = 0               # streaming reads of D3 actually performed (n_sweeps + 1)
+
+
+def future_cost(D3: torch.Tensor, alpha: float = 0.997, row0: int = 0, m: int | None = None,
+                exchange=None, pad_to: int | None = None, verbose: bool = False,
+                max_sweeps: int = 10000) -> FutureCostResult:
+    """K3 loop.  D3 holds global rows [row0, row0+rows) (rows may include a halo row: pass `rows`
+    via slicing before the call).  `exchange(m_vec, eps_buf)` (multi-GPU) must all-gather the
+    per-row minima in place and all-reduce the eps numerator; None on a single GPU.
+    One host read of eps per sweep is inherent: the reference's stop rule is data dependent.
+    """
+    rows = D3.shape[0]
+    m = D3.shape[1] if m is None else m
+    length = m if pad_to is None else pad_to
+    dev, st = _dev(D3), _stream(D3)
+    bufs = [torch.zeros(length, dtype=torch.float32, device=D3.device) for _ in range(3)]
+    eps_buf = torch.zeros(1, dtype=torch.float64, device=D3.device)
+    alpha32 = C.c_float(_f32(alpha))
+
+    def sweep(prev, prev2, out, eps):
+        _lib.call("avtex_future_cost_sweep", _lib.ptr(D3), D3.stride(0), row0, rows, m, _lib.ptr(prev),
+                  _lib.ptr(prev2), alpha32, _lib.ptr(out), _lib.ptr(eps), dev, st)
+
+    sweep(None, None, bufs[0], None)                       # pass 0: m^0 = row minima of D3
+    if exchange is not None:
+        exchange(bufs[0], None)
+    cur, prev2 = bufs[0], None
+    free = [bufs[1], bufs[2]]
+    trail = []
+    for p in range(1, max_sweeps + 1):
+        out = free.pop()
+        eps_buf.zero_()
+        sweep(cur, prev2, out, eps_buf)                    # m^p and the eps numerator of sweep p
+        if exchange is not None:
+            exchange(out, eps_buf)
+        eps = np.float32(eps_buf.item() / (float(m) * float(m)))
+        trail.append(float(eps))
+        if verbose:
+            print("Eps:", f"tensor({eps:.4f}, device='{D3.device}')")
+        if not (eps > np.float32(F32_EPS_STOP)):
+            return FutureCostResult(cur, p, trail, p + 1)
+        if prev2 is not None:
+            free.append(prev2)
+        prev2, cur = cur, out
+    raise RuntimeError("future cost did not converge")
+
+
+def future_cost_finalize(D3: torch.Tensor, mvec: torch.Tensor, alpha: float = 0.997, row0: int = 0,
+                         m: int | None = None, stats: torch.Tensor | None = None) -> torch.Tensor:
+    rows = D3.shape[0]
+    m = D3.shape[1] if m is None else m
+    out = torch.empty((rows, m), dtype=torch.float32, device=D3.device)
+    s, z = _stats_ptrs(stats)
+    _lib.call("avtex_future_cost_finalize", _lib.ptr(D3), D3.stride(0), row0, rows, m, _lib.ptr(mvec),
+              C.c_float(_f32(alpha)), _lib.ptr(out), m, s, z, _dev(D3), _stream(D3))
+    return out
+
+
+# --------------------------------------------------------------------------- K6 / K7
+def l2_normalize_rows(x: torch.Tensor) -> torch.Tensor:
+    x = x if x.stride(-1) == 1 else x.contiguous()
+    y = torch.empty(x.shape, dtype=torch.float32, device=x.device)
+    _lib.call("avtex_l2_normalize_rows", _lib.ptr(x), x.stride(0), x.shape[0], x.shape[1], _lib.ptr(y),
+              y.stride(0), _dev(x), _stream(x))
+    return y
+
+
+def cosine_scores(tn: torch.Tensor, qn: torch.Tensor, temp: float, out: torch.Tensor | None = None):
+    out = torch.empty(tn.shape[0], dtype=torch.float32, device=tn.device) if out is None else out
+    _lib.call("avtex_cosine_scores", _lib.ptr(tn), tn.stride(0), tn.shape[0], tn.shape[1], _lib.ptr(qn),
+              C.c_float(_f32(temp)), _lib.ptr(out), _dev(tn), _stream(tn))
+    return out
+
+
+def select_step(o: torch.Tensor, a: torch.Tensor | None, q: int, alpha: float, threshold: float,
+                choices: torch.Tensor, n_choices: torch.Tensor, vals: torch.Tensor | None = None):
+    """K7.  `choices` (int32 [L]) / `n_choices` (int32 [1]) are caller-owned device buffers."""
+    _lib.call("avtex_select_step", _lib.ptr(o), _lib.ptr(a), o.shape[0], int(q), C.c_float(_f32(alpha)),
+              C.c_float(np.float32(1.0 - float(alpha))), C.c_float(_f32(threshold)), _lib.ptr(choices),
+              _lib.ptr(n_choices), _lib.ptr(vals), _dev(o), _stream(o))
+
+
+def audio_start(x: torch.Tensor, d: torch.Tensor) -> int:
+    """a10: start window = first arg-max of the cosine similarity to the first driving example."""
+    x = x if x.stride(-1) == 1 else x.contiguous()
+    ws = torch.empty(x.shape[0], dtype=torch.float32, device=x.device)
+    out = torch.zeros(1, dtype=torch.int32, device=x.device)
+    _lib.call("avtex_audio_start", _lib.ptr(x), x.stride(0), x.shape[0], x.shape[1], _lib.ptr(d.contiguous()),
+              _lib.ptr(ws), _lib.ptr(out), _dev(x), _stream(x))
+    return int(out.item())
+
+
+def gram_tile_schedule(TM: int, TN: int, symmetric: bool):
+    """Test hook (host only, no GPU): visiting order of the Gram tiles."""
+    lib = _lib.load()
+    total = lib.avtex_gram_tile_schedule(TM, TN, 1 if symmetric else 0, None, None, 0)
+    tm = (C.c_int * total)()
+    tn = (C.c_int * total)()
+    lib.avtex_gram_tile_schedule(TM, TN, 1 if symmetric else 0, tm, tn, total)
+    return list(zip(tm, tn))

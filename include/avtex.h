@@ -1,0 +1,175 @@
+/*
+ * avtex.h — C ABI of libavtex.so: the B200 (sm_100a) transition-matrix engine.
+ *
+ * The reference (medhini/audio-video-textures) is pure Python/PyTorch and has no FFI or plugin
+ * interface; its hot path sits behind Python callables.  Each entry point below replaces the
+ * tensor arithmetic of one of those callables; the "replaces:" line cites the reference code
+ * (paths relative to the reference root; classic/ = baselines/classic_video_textures/,
+ * cvt/ = contrastive_video_textures/).  INTEGRATION.md shows the ctypes binding a maintainer adds.
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on failure; avtex_last_error() then returns
+ *     a thread-local, NUL-terminated message.  Nothing throws across the ABI.
+ *   - all pointers are DEVICE pointers on `device` unless the name starts with h_.
+ *   - matrices are row-major with an explicit leading dimension in ELEMENTS.
+ *   - `stream` is a cudaStream_t (pass torch.cuda.current_stream().cuda_stream); every call is
+ *     asynchronous on it and performs no host synchronisation unless stated.
+ *   - accumulators (`double *sum`, `unsigned long long *nnz`, ...) are ADDED to: zero them first
+ *     (avtex_zero) — this is what lets row-shards and fused stages share one accumulator.
+ *   - no hidden allocation: workspaces are caller-provided.
+ */
+#ifndef AVTEX_H_
+#define AVTEX_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AVTEX_ABI_VERSION 1
+#if defined(__GNUC__)
+#define AVTEX_API __attribute__((visibility("default")))
+#else
+#define AVTEX_API
+#endif
+
+AVTEX_API int avtex_abi_version(void);
+AVTEX_API const char *avtex_last_error(void);
+/* Number of SMs / compute capability major*10+minor of `device` (host query, no stream). */
+AVTEX_API int avtex_device_info(int device, int *sm_count, int *cc);
+/* cudaMemsetAsync(ptr, 0, bytes). */
+AVTEX_API int avtex_zero(void *ptr, int64_t bytes, int device, void *stream);
+
+/* ---------------------------------------------------------------- K0: frame packing + norms
+ * Packs frames [n, k] into centred signed bytes  packed[i, c] = frames[i, c] - 128  (zero padded to
+ * kp columns, kp % 128 == 0) and writes the exact squared norms sqnorm[i] = sum_c packed[i,c]^2.
+ * Pixel distances are translation invariant, so the centring changes no result; it keeps the
+ * int32 tensor-core accumulator of avtex_gram_l2_s8 inside its range.
+ * The f32 variant requires integer-valued inputs in [0, 255] (a uint8-derived video as float);
+ * it sets flags[0] = 1 if any element is not, and the caller must then use
+ * avtex_pairdist_direct_f32.
+ * replaces: the operand staging of classic/computeD1.py:61-83 (`frames[i:i+bs].cuda()`, repeat, view).
+ */
+AVTEX_API int avtex_pack_frames_u8(const uint8_t *frames, int64_t n, int64_t k, int64_t ld,
+                         int8_t *packed, int64_t kp, int64_t *sqnorm, int device, void *stream);
+AVTEX_API int avtex_pack_frames_f32(const float *frames, int64_t n, int64_t k, int64_t ld,
+                          int8_t *packed, int64_t kp, int64_t *sqnorm, int *flags,
+                          int device, void *stream);
+
+/* ---------------------------------------------------------------- K1: pairwise L2 distances
+ * D[(r - row0), j] = sqrt( sqnorm[r] + sqnorm[j] - 2 * <packed[r], packed[j]> ),  r in [row0, row0+rows),
+ * j in [0, n).  The Gram is computed on tcgen05 (kind::i8, s8 x s8 -> s32 in TMEM) from TMA-fed
+ * 128B-swizzled shared-memory tiles; the norm/sqrt epilogue is fused; d^2 is an exact integer so
+ * duplicate frames give exactly 0 (the reference counts `nonzero(D1)`).  If `sum`/`nnz` are non-NULL
+ * the fp64 sum and the non-zero count of the written block are added to them.
+ * `symmetric` != 0 (requires row0 == 0, rows == n): only tiles on/above the diagonal are computed
+ * and mirrored.  Precondition (checked by the host wrapper): 4 * max(sqnorm) < 2^32.
+ * replaces: classic/computeD1.py:50-56 (dense) and :58-96 (tiled "slow" path), RGB branch.
+ */
+AVTEX_API int avtex_gram_l2_s8(const int8_t *packed, int64_t n, int64_t kp, const int64_t *sqnorm,
+                     int64_t row0, int64_t rows, int symmetric, float *D, int64_t ldd,
+                     double *sum, unsigned long long *nnz, int device, void *stream);
+
+/* Same contract by direct difference in fp32 (the reference's own formula), for arbitrary float
+ * features; SIMT, no tensor cores.  x is [n, k] fp32. */
+AVTEX_API int avtex_pairdist_direct_f32(const float *x, int64_t n, int64_t k, int64_t ld,
+                              int64_t row0, int64_t rows, float *D, int64_t ldd,
+                              double *sum, unsigned long long *nnz, int device, void *stream);
+AVTEX_API int avtex_pairdist_direct_u8(const uint8_t *x, int64_t n, int64_t k, int64_t ld,
+                             int64_t row0, int64_t rows, float *D, int64_t ldd,
+                             double *sum, unsigned long long *nnz, int device, void *stream);
+
+/* ---------------------------------------------------------------- statistics for sigma
+ * sum += fp64 sum of D[rows, cols];  nnz += #{D != 0}.
+ * replaces: `torch.nonzero(D).size(0)` and `D.sum()` of classic/computeD1.py:240-241,
+ * classic/computeD2.py:44-45, classic/q_learning.py:53-54.
+ */
+AVTEX_API int avtex_sum_nnz(const float *D, int64_t rows, int64_t cols, int64_t ld,
+                  double *sum, unsigned long long *nnz, int device, void *stream);
+
+/* ---------------------------------------------------------------- K2: diagonal temporal filter
+ * D2[a - a0, b] = sum_{k<fs} w[k] * D1[a*stride + k - in_row0, b*stride + k]   (k ascending, fp32)
+ * for a in [a0, a0 + rows_out), b in [0, m).  `D1` points at global row `in_row0` of the distance
+ * matrix and holds `in_rows` rows (row shards pass their halo'd block).  If D3 != NULL also writes D3 = powf(D2, p).
+ * sum/nnz (nullable) accumulate the stats of the D2 rows written.
+ * h_w: HOST pointer to the fs fp32 taps (passed to the kernel by value; fs <= 64 takes the
+ * register-resident path, larger fs a generic path).
+ * replaces: classic/computeD2.py:34-42 (F.conv2d with diag(binomial)) and classic/q_learning.py:34 (D2 ** p).
+ */
+AVTEX_API int avtex_diag_filter_pow(const float *D1, int64_t ld1, int64_t in_row0, int64_t in_rows, const float *h_w, int fs,
+                          int stride, int64_t a0, int64_t rows_out, int64_t m,
+                          float *D2, int64_t ld2, float *D3, int64_t ld3, float p,
+                          double *sum, unsigned long long *nnz, int device, void *stream);
+
+/* ---------------------------------------------------------------- K3/K4: future cost
+ * One Jacobi sweep in vector form.  For the rows j in [row0, row0+rows) of D3
+ * (pointer at row `row0`, m columns):
+ *     m_new[j] = min_{k != j} ( D3[j,k] + fl(alpha * m_prev[k]) )     j >= 1   (m_prev == NULL: + 0)
+ *     m_new[0] = min_{k != 0}   D3[0,k]
+ * and, if eps_sum != NULL, adds  sum_{j>=1,k} ( fl(D3+fl(alpha*m_prev)) - X_prev )^2  with
+ * X_prev = fl(D3 + fl(alpha*m_prev2)) (or D3 when m_prev2 == NULL): the numerator of the
+ * reference's `eps` for the sweep that produced m_prev.
+ * replaces: classic/q_learning.py:39-50.
+ */
+AVTEX_API int avtex_future_cost_sweep(const float *D3, int64_t ld, int64_t row0, int64_t rows, int64_t m,
+                            const float *m_prev, const float *m_prev2, float alpha,
+                            float *m_new, double *eps_sum, int device, void *stream);
+/* D3_new[j,:] = D3[j,:] + fl(alpha * mvec)  (j >= 1),  row 0 copied.  sum/nnz nullable.
+ * replaces: the materialised D3_new of classic/q_learning.py:48 at convergence. */
+AVTEX_API int avtex_future_cost_finalize(const float *D3, int64_t ld, int64_t row0, int64_t rows, int64_t m,
+                               const float *mvec, float alpha, float *D3_new, int64_t ld_out,
+                               double *sum, unsigned long long *nnz, int device, void *stream);
+
+/* ---------------------------------------------------------------- K5: transition probabilities
+ * For output rows i in [0, rows_out): source row r = min(i + shift, rows_in - 1) of D,
+ *     P[i,:] = exp(-D[r,:] / sigma) / rowsum,   P_new = (P < max_i - fl(th*max_i)) ? 0 : P.
+ * P and P_new are nullable (P_new requires th >= 0).  counts (nullable) receives #nonzero of
+ * P_new (or of P when P_new == NULL) per row.
+ * replaces: classic/computeD1.py:242-245, classic/computeD2.py:47-50, classic/q_learning.py:56-64.
+ */
+AVTEX_API int avtex_transition_probs(const float *D, int64_t ld, int64_t rows_in, int64_t cols, float sigma,
+                           int shift, int64_t rows_out, float *P, int64_t ldp, float th,
+                           float *P_new, int64_t ldn, int *counts, int device, void *stream);
+
+/* Non-zero structure of a matrix (ascending columns inside each row): the survivor lists the
+ * sampling walk draws from.  counts[r] = #nonzero(row r);  colidx[rowptr[r] + t] = t-th non-zero.
+ * replaces: `P[this_frame].nonzero().view(-1).detach().cpu()` per step,
+ * classic/video_textures.py:76-78,149-151,186-188. */
+AVTEX_API int avtex_row_nnz(const float *P, int64_t ld, int64_t rows, int64_t cols, int *counts,
+                  int device, void *stream);
+AVTEX_API int avtex_csr_fill(const float *P, int64_t ld, int64_t rows, int64_t cols, const int64_t *rowptr,
+                   int *colidx, int device, void *stream);
+
+/* ---------------------------------------------------------------- K6/K7: contrastive synthesis
+ * y[i,:] = x[i,:] / max(||x[i,:]||_2, 1e-12).
+ * replaces: nn.functional.normalize of cvt/models/models.py:351,412,433,436. */
+AVTEX_API int avtex_l2_normalize_rows(const float *x, int64_t ld, int64_t rows, int64_t dim,
+                            float *y, int64_t ldy, int device, void *stream);
+/* out[w] = <qn, tn[w,:]> / temp  for w in [0, rows) — one query against every window.
+ * replaces: torch.bmm(q, t).squeeze(1) / temp of cvt/models/models.py:416-417 (and :439,457). */
+AVTEX_API int avtex_cosine_scores(const float *tn, int64_t ld, int64_t rows, int64_t dim, const float *qn,
+                        float temp, float *out, int device, void *stream);
+/* One selection step over the target list ids = [pos] ++ ascending({0..L-1} \ {q, pos}),
+ * pos = min(q+1, L-1):   o /= sum(o);  a /= sum(a);  v = alpha*o + (1-alpha)*a  (a == NULL: v = o);
+ * v[v < max - fl(th*max)] = 0;  v[nz] /= sum(v);  choices = window ids of the non-zeros in ids order.
+ * one_minus_alpha is passed separately because the reference evaluates (1 - alpha) in float64.
+ * vals (nullable, length L): the final v in window order (entry q undefined unless q == L-1).
+ * replaces: cvt/validate.py:369-378, 524-527, 554, 558, 568. */
+AVTEX_API int avtex_select_step(const float *o, const float *a, int64_t L, int64_t q, float alpha,
+                      float one_minus_alpha, float th, int *choices, int *n_choices, float *vals,
+                      int device, void *stream);
+/* out[0] = arg max_w <normalize(x[w,:]), normalize(d)> with strict '>' against a running max that
+ * starts at 0 (first maximum wins; 0 if no similarity is positive).
+ * replaces: the start-segment search of cvt/validate.py:222-240. */
+AVTEX_API int avtex_audio_start(const float *x, int64_t ld, int64_t rows, int64_t dim, const float *d,
+                      float *sims_ws, int *out, int device, void *stream);
+
+/* Test hook: the tile visiting order of avtex_gram_l2_s8 for TM x TN tiles (128 x 256).  Returns the
+ * number of tiles; fills tm_out/tn_out (capacity entries) when non-NULL.  Host only. */
+AVTEX_API int avtex_gram_tile_schedule(int TM, int TN, int symmetric, int *tm_out, int *tn_out, int capacity);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AVTEX_H_ */

@@ -1,0 +1,285 @@
+"""GPU parity tests (B200): every kernel of the classic path through the C ABI against the golden
+vectors of the unmodified reference and against the CPU oracle on the same inputs.
+
+Tolerances: integer / index work bit-exact; order-free fp32 work (future-cost sweeps, thresholds on
+given probabilities) bit-exact; everything that involves a reduction order or exp/pow is held to
+rtol 1e-4 (BASELINE.json north_star), most of it to 1e-5.
+"""
+import numpy as np
+import pytest
+import torch
+
+from conftest import CLASSIC_GOLDEN, load_golden
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-4
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from audio_video_textures_b200 import engine
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return engine
+
+
+def _csr_of(P):
+    rows, cols = torch.nonzero(P, as_tuple=True)
+    counts = torch.bincount(rows, minlength=P.shape[0])
+    return torch.cat((torch.zeros(1, dtype=torch.long), counts.cumsum(0))).numpy(), cols.numpy()
+
+
+# ----------------------------------------------------------------------------- K0 / K1
+@pytest.mark.parametrize("name", CLASSIC_GOLDEN)
+def test_direct_distance_matches_reference(eng, name):
+    g = load_golden(name)
+    video = torch.from_numpy(g["video"]).cuda()
+    stats = eng.new_stats(video.device)
+    D = eng.pairdist_direct(video.float(), stats=stats)
+    np.testing.assert_allclose(D.cpu().numpy(), g["ref_D1"], rtol=1e-5)
+    Du8 = eng.pairdist_direct(video)
+    assert torch.equal(D, Du8)
+    total, nnz = eng.read_stats(stats)
+    assert nnz == int((g["ref_D1"] != 0).sum())
+    np.testing.assert_allclose(total, g["ref_D1"].astype(np.float64).sum(), rtol=1e-5)
+
+
+@pytest.mark.parametrize("name", CLASSIC_GOLDEN)
+def test_pack_frames_exact(eng, name):
+    g = load_golden(name)
+    video = torch.from_numpy(g["video"])
+    x = video.reshape(video.shape[0], -1)
+    pf = eng.pack_frames(video.cuda())
+    assert pf.exact_ok
+    ref = (x.to(torch.int16) - 128).to(torch.int8)
+    assert torch.equal(pf.packed[:, :x.shape[1]].cpu(), ref)
+    assert int(pf.packed[:, x.shape[1]:].abs().sum()) == 0
+    assert torch.equal(pf.sqnorm.cpu(), (ref.to(torch.int64) ** 2).sum(1))
+    pf32 = eng.pack_frames(video.float().cuda())
+    assert pf32.exact_ok and torch.equal(pf32.packed, pf.packed) and torch.equal(pf32.sqnorm, pf.sqnorm)
+    bad = video.float().cuda()
+    bad[3, 0, 0, 0] = 17.5
+    assert not eng.pack_frames(bad).exact_ok
+
+
+@pytest.mark.parametrize("name", CLASSIC_GOLDEN)
+def test_gram_distance_exact_and_within_tolerance(eng, name):
+    from oracle import classic
+    g = load_golden(name)
+    video = torch.from_numpy(g["video"])
+    pf = eng.pack_frames(video.cuda())
+    stats = eng.new_stats("cuda")
+    D = eng.gram_l2(pf, stats=stats)
+    torch.cuda.synchronize()
+    Dh = D.cpu()
+    exact = classic.pairwise_l2_exact_u8(video)
+    # d^2 is an exact integer on the GPU; only the final fp32 sqrt rounds
+    np.testing.assert_allclose(Dh.numpy(), exact.numpy(), rtol=2e-7, atol=0)
+    assert torch.equal(Dh, Dh.T) and float(Dh.diagonal().abs().max()) == 0.0
+    assert np.array_equal(Dh.numpy() == 0, g["ref_D1"] == 0)
+    np.testing.assert_allclose(Dh.numpy(), g["ref_D1"], rtol=RTOL)
+    total, nnz = eng.read_stats(stats)
+    assert nnz == int((Dh != 0).sum())
+    np.testing.assert_allclose(total, Dh.double().sum().item(), rtol=1e-12)
+    # row-block (non-symmetric) mode reproduces the same values: what a row shard computes
+    n = video.shape[0]
+    r0, rows = n // 3, n // 2
+    Db = eng.gram_l2(pf, r0, rows)
+    assert torch.equal(Db.cpu(), Dh[r0:r0 + rows])
+    # against the direct-difference kernel on the same device
+    Dd = eng.pairdist_direct(video.cuda())
+    np.testing.assert_allclose(Dh.numpy(), Dd.cpu().numpy(), rtol=1e-5)
+
+
+def test_gram_edge_shapes(eng):
+    """Ragged N (not a multiple of the 128 x 256 tile), K not a multiple of 128, duplicate frames,
+    a single K block, and N smaller than one tile."""
+    from oracle import classic
+    gen = torch.Generator().manual_seed(5)
+    for n, k in [(1, 7), (2, 128), (130, 100), (257, 384), (300, 1000), (515, 129)]:
+        x = torch.randint(0, 256, (n, k), dtype=torch.uint8, generator=gen)
+        if n > 5:
+            x[5] = x[2]                        # duplicate -> exact zero off the diagonal
+        pf = eng.pack_frames(x.cuda())
+        D = eng.gram_l2(pf).cpu()
+        exact = classic.pairwise_l2_exact_u8(x)
+        np.testing.assert_allclose(D.numpy(), exact.numpy(), rtol=2e-7)
+        if n > 5:
+            assert D[5, 2] == 0 and D[2, 5] == 0
+
+
+def test_gram_domain_guard_and_extreme_values(eng):
+    """The epilogue evaluates d^2 modulo 2^32.  The host wrapper only takes the tensor-core path when
+    4*max(n) < 2^32, which bounds every prefix of <x,y> by 2^30 (Cauchy-Schwarz) and d^2 by 2^32, so
+    nothing can wrap; black-vs-white frames at K = 150528 (d^2 = K*255^2 > 2^32) must be routed to the
+    direct kernel, and large-but-legal norms at the same K must stay exact."""
+    from oracle import classic
+    k = 150528
+    x = torch.zeros((4, k), dtype=torch.uint8)
+    x[1] = 255
+    x[2] = 200
+    x[3, ::2] = 255
+    pf = eng.pack_frames(x.cuda())
+    assert not pf.exact_ok
+    with pytest.raises(Exception):
+        eng.pairwise_l2(x.cuda(), method="gram")
+    D, used = eng.pairwise_l2(x.cuda())
+    assert used == "direct"
+    np.testing.assert_allclose(D.cpu().numpy(), classic.pairwise_l2_exact_u8(x).numpy(), rtol=1e-5)
+    y = torch.full((3, k), 128, dtype=torch.uint8)
+    y[0] = 128 + 84                                           # n = K*84^2 = 1.06e9: 4n just below 2^32
+    y[1] = 128 + 80
+    y[2] = 128 - 80
+    pf = eng.pack_frames(y.cuda())
+    assert pf.exact_ok
+    Dg = eng.gram_l2(pf).cpu()
+    np.testing.assert_allclose(Dg.numpy(), classic.pairwise_l2_exact_u8(y).numpy(), rtol=2e-7)
+
+
+# ----------------------------------------------------------------------------- K2
+@pytest.mark.parametrize("name", CLASSIC_GOLDEN)
+def test_diag_filter_matches_reference(eng, name):
+    from oracle import classic
+    g = load_golden(name)
+    fs, stride = int(g["fs"]), int(g["stride"])
+    D1 = torch.from_numpy(g["ref_D1"]).cuda()
+    stats = eng.new_stats("cuda")
+    D2, D3 = eng.diag_filter(D1, fs, stride, p=0.7, stats=stats)
+    np.testing.assert_allclose(D2.cpu().numpy(), g["ref_D2"], rtol=1e-5)
+    seq = classic.diag_filter_sequential(torch.from_numpy(g["ref_D1"]), fs, stride)
+    np.testing.assert_allclose(D2.cpu().numpy(), seq.numpy(), rtol=2e-6)
+    np.testing.assert_allclose(D3.cpu().numpy(), (D2.cpu() ** 0.7).numpy(), rtol=1e-5)
+    total, nnz = eng.read_stats(stats)
+    assert nnz == int((D2 != 0).sum())
+    np.testing.assert_allclose(total, D2.double().sum().item(), rtol=1e-12)
+    np.testing.assert_array_equal(eng.binomial_taps(fs), g["ref_filter_diag"])
+    # row-sharded call with a halo'd D1 block gives the same rows
+    m = D2.shape[0]
+    a0, rows = m // 3, m // 4
+    lo, hi = a0 * stride, (a0 + rows - 1) * stride + fs
+    part, _ = eng.diag_filter(D1[lo:hi], fs, stride, m=m, a0=a0, rows_out=rows, in_row0=lo)
+    assert torch.equal(part, D2[a0:a0 + rows])
+
+
+@pytest.mark.parametrize("fs,stride,n", [(5, 2, 61), (3, 3, 40), (70, 1, 200), (1, 1, 33), (16, 4, 100),
+                                         (8, 1, 9), (40, 4, 43)])
+def test_diag_filter_generic_and_edge(eng, fs, stride, n):
+    from oracle import classic
+    gen = torch.Generator().manual_seed(fs * 100 + stride)
+    D1 = torch.rand(n, n, generator=gen) * 100
+    D2, _ = eng.diag_filter(D1.cuda(), fs, stride)
+    ref = classic.compute_D2(D1, torch.tensor(4.5), fs, stride)[0]
+    assert D2.shape == ref.shape
+    np.testing.assert_allclose(D2.cpu().numpy(), ref.numpy(), rtol=1e-5)
+
+
+# ----------------------------------------------------------------------------- K3 / K4
+@pytest.mark.parametrize("name", CLASSIC_GOLDEN)
+def test_future_cost_bit_exact(eng, name):
+    from oracle import classic
+    g = load_golden(name)
+    D3 = torch.from_numpy(g["ref_D2"]) ** 0.7                  # same D3 on both sides
+    want, trail = classic.future_cost(D3)
+    fc = eng.future_cost(D3.cuda())
+    assert fc.n_sweeps == int(g["ref_n_sweeps"]) == len(trail)
+    stats = eng.new_stats("cuda")
+    got = eng.future_cost_finalize(D3.cuda(), fc.mvec, stats=stats)
+    assert torch.equal(got.cpu(), want)                        # min / single rounded add: order-free
+    np.testing.assert_array_equal(got.cpu().numpy(), g["ref_D3_new"])
+    np.testing.assert_allclose(fc.eps_trail, trail, rtol=1e-5, atol=1e-12)
+    for e in fc.eps_trail:                                     # stop decision is not marginal
+        assert abs(e - 0.01) / 0.01 > 1e-3
+    total, nnz = eng.read_stats(stats)
+    sigma = eng.sigma_from_stats(total, nnz, g["sigma_factor"])
+    np.testing.assert_allclose(sigma, g["ref_sigma3"], rtol=1e-6)
+
+
+def test_future_cost_unaligned_rows_and_row_blocks(eng):
+    """Odd M (rows not 16-byte aligned -> scalar path) and the row-sharded call pattern."""
+    from oracle import classic
+    gen = torch.Generator().manual_seed(3)
+    M = 203
+    D3 = (torch.rand(M, M, generator=gen) * 50 + 1)
+    want, trail = classic.future_cost(D3)
+    d = D3.cuda()
+    fc = eng.future_cost(d)
+    assert fc.n_sweeps == len(trail)
+    assert torch.equal(eng.future_cost_finalize(d, fc.mvec).cpu(), want)
+    # one sweep computed in two row blocks == one block
+    m0 = torch.zeros(M, device="cuda")
+    import ctypes as C
+    from audio_video_textures_b200 import _lib
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    for r0, rows in ((0, 100), (100, 103)):
+        blk = d[r0:r0 + rows]
+        _lib.call("avtex_future_cost_sweep", _lib.ptr(blk), blk.stride(0), r0, rows, M, None, None,
+                  C.c_float(0.997), _lib.ptr(m0), None, 0, st)
+    assert torch.equal(m0.cpu(), classic.row_min_offdiag(D3))
+
+
+# ----------------------------------------------------------------------------- K5 + CSR + walk
+@pytest.mark.parametrize("name", CLASSIC_GOLDEN)
+def test_transition_probs_threshold_and_walk(eng, name):
+    from audio_video_textures_b200.classic.video_textures import texture_walk
+    g = load_golden(name)
+    th = float(g["threshold"])
+    D3n = torch.from_numpy(g["ref_D3_new"]).cuda()
+    P3, P3n, counts = eng.transition_probs(D3n, g["ref_sigma3"], threshold=th, want_counts=True)
+    np.testing.assert_allclose(P3.cpu().numpy(), g["ref_P3"], rtol=1e-5)
+    np.testing.assert_allclose(P3.sum(1).cpu().numpy(), 1.0, rtol=1e-5)
+    rowptr, cols = eng.csr_from_matrix(P3n, counts)
+    np.testing.assert_array_equal(rowptr, g["ref_P3new_rowptr"])     # survivor sets: bit-exact
+    np.testing.assert_array_equal(cols, g["ref_P3new_cols"])
+    rp2, c2 = eng.csr_from_matrix(P3n)                                # count kernel path
+    np.testing.assert_array_equal(rp2, rowptr)
+    kept = P3n != 0
+    assert torch.equal(P3n[kept], P3[kept])                           # not renormalised (q_learning.py:64)
+    np.random.seed(int(g["seed"]))
+    frames, jumps = texture_walk(P3n, int(g["model_type"]), int(g["fps"]), int(g["nvl"]), int(g["stride"]),
+                                 int(g["fs"]))
+    np.testing.assert_array_equal(np.array(frames), g["walk_frames"])
+    assert jumps == int(g["walk_jump_count"])
+
+
+# ----------------------------------------------------------------------------- drop-in, end to end
+@pytest.mark.parametrize("name", CLASSIC_GOLDEN)
+def test_dropin_pipeline_end_to_end(eng, name, capsys):
+    """video -> compute_D1 -> compute_D2 -> q_learning -> walk through the reference-named entry
+    points; values rtol 1e-4, survivor sets and the emitted frame sequence bit-exact."""
+    from audio_video_textures_b200.classic import q_learning as ql_mod
+    from audio_video_textures_b200.classic.computeD1 import compute_D1
+    from audio_video_textures_b200.classic.computeD2 import compute_D2
+    from audio_video_textures_b200.classic.q_learning import q_learning
+    from audio_video_textures_b200.classic.video_textures import texture_walk
+    g = load_golden(name)
+    f = torch.tensor(float(g["sigma_factor"]), dtype=torch.float32)
+    fs, stride, th, m = int(g["fs"]), int(g["stride"]), float(g["threshold"]), int(g["model_type"])
+    frames = torch.from_numpy(g["video"]).float()                 # what a float `read_data` would hand over
+    D1, P1, s1 = compute_D1(frames, f, "RGB", slow=True, batch_size=48)
+    assert D1.is_cuda and P1.is_cuda and s1.is_cuda and s1.dim() == 0
+    np.testing.assert_allclose(D1.cpu().numpy(), g["ref_D1"], rtol=RTOL)
+    np.testing.assert_allclose(s1.item(), g["ref_sigma1"], rtol=RTOL)
+    np.testing.assert_allclose(P1[0].cpu().numpy(), g["ref_P1_row0"], rtol=RTOL)
+    if m in (1, 2):
+        D2, P2, s2, bf = compute_D2(D1, f, filter_size=fs)
+    else:
+        D2, P2, s2, bf = compute_D2(D1, f, filter_size=fs, stride=stride)
+    assert tuple(bf.shape) == (1, 1, fs, fs)
+    np.testing.assert_allclose(D2.cpu().numpy(), g["ref_D2"], rtol=RTOL)
+    np.testing.assert_allclose(s2.item(), g["ref_sigma2"], rtol=RTOL)
+    np.testing.assert_allclose(P2[0].cpu().numpy(), g["ref_P2_row0"], rtol=RTOL)
+    D2_before = D2.clone()
+    D3n, P3, P3n, s3 = q_learning(D2, f, thresholding=th)
+    assert torch.equal(D2, D2_before)
+    out = capsys.readouterr().out
+    assert out.count("Eps:") == int(g["ref_n_sweeps"]) and "Non Zero in P3:" in out
+    np.testing.assert_allclose(D3n.cpu().numpy(), g["ref_D3_new"], rtol=RTOL)
+    np.testing.assert_allclose(s3.item(), g["ref_sigma3"], rtol=RTOL)
+    np.testing.assert_allclose(P3.cpu().numpy(), g["ref_P3"], rtol=RTOL)
+    rowptr, cols = eng.csr_from_matrix(P3n)
+    np.testing.assert_array_equal(rowptr, g["ref_P3new_rowptr"])
+    np.testing.assert_array_equal(cols, g["ref_P3new_cols"])
+    np.random.seed(int(g["seed"]))
+    frames_out, jumps = texture_walk(P3n, m, int(g["fps"]), int(g["nvl"]), stride, fs)
+    np.testing.assert_array_equal(np.array(frames_out), g["walk_frames"])
+    assert jumps == int(g["walk_jump_count"]) and ql_mod.LAST["n_sweeps"] == int(g["ref_n_sweeps"])
