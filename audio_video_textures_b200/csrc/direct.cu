@@ -1,7 +1,12 @@
 // K1 (fallback) — pairwise L2 by direct difference, the reference's own formula
 // (classic/computeD1.py:88: torch.norm(feats_A - feats_B, dim=2)), fp32 SIMT.
-// Used for features that are not integer-valued bytes and as the on-device cross-check of the
-// tensor-core Gram path.  FP32-pipe bound: 2 instructions (sub, fma) per (pair, feature).
+// Used for features that are not integer-valued bytes, for byte frames outside the Gram path's
+// d^2 < 2^32 domain, and as the on-device cross-check of the tensor-core path.
+// FP32-pipe bound: 2 instructions (sub, fma) per (pair, feature).
+// Accumulation is two-level: each 32-feature stage is summed in fp32 and the stage sums are added
+// in fp64.  A single running fp32 sum drifts by ~5e-5 at K = 12288 (measured), more than the
+// reference's vectorised torch.norm; two-level keeps it below 1e-6, and for byte inputs every
+// stage sum is an integer < 2^24, so the result is the exact d^2 (bit-identical to the Gram path).
 #include "common.cuh"
 
 namespace {
@@ -22,11 +27,11 @@ pairdist_direct_kernel(const T *__restrict__ x, int64_t n, int64_t k, int64_t ld
     const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
     const int64_t ra0 = row0 + int64_t(blockIdx.y) * DT;     // global row of A tile
     const int64_t rb0 = int64_t(blockIdx.x) * DT;            // global row of B tile (= output column)
-    float acc[4][4];
+    double acc[4][4];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
 
     for (int64_t k0 = 0; k0 < k; k0 += DK) {
         for (int idx = threadIdx.x; idx < DT * DK; idx += DTHREADS) {
@@ -37,6 +42,11 @@ pairdist_direct_kernel(const T *__restrict__ x, int64_t n, int64_t k, int64_t ld
             Bs[c][r] = (gb < n && kc < k) ? float(x[gb * ld + kc]) : 0.f;
         }
         __syncthreads();
+        float part[4][4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) part[i][j] = 0.f;
 #pragma unroll 8
         for (int kk = 0; kk < DK; ++kk) {
             float a[4], b[4];
@@ -47,9 +57,13 @@ pairdist_direct_kernel(const T *__restrict__ x, int64_t n, int64_t k, int64_t ld
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     const float d = a[i] - b[j];
-                    acc[i][j] = fmaf(d, d, acc[i][j]);
+                    part[i][j] = fmaf(d, d, part[i][j]);
                 }
         }
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[i][j] += (double)part[i][j];
         __syncthreads();
     }
     double s = 0.0;
@@ -62,7 +76,7 @@ pairdist_direct_kernel(const T *__restrict__ x, int64_t n, int64_t k, int64_t ld
         for (int j = 0; j < 4; ++j) {
             const int64_t gc = rb0 + tx * 4 + j;
             if (gc >= n) continue;
-            const float d = sqrtf(acc[i][j]);
+            const float d = __fsqrt_rn(__double2float_rn(acc[i][j]));   // same rounding sequence as gram.cu
             D[(gr - row0) * ldd + gc] = d;
             s += d;
             z += (d != 0.f);
