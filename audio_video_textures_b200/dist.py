@@ -1,0 +1,138 @@
+"""Row-sharded classic++ transition matrix over the GPUs of one box (one process per GPU).
+
+Rank r owns rows [a0, a1) of every M x M matrix (D2, D3, D3_new, P3) and the D1 rows those need
+(`a*stride + k`, plus one halo output row for the row shift of P, over-computed locally instead of
+exchanged: ~fs extra D1 rows out of N/G).  Frames are replicated (N*K bytes, 1.2 GB at N = 100k,
+64x64).  The ONLY data-path exchange is the one the algorithm has: after each future-cost sweep
+the per-row minima (M fp32) are all-gathered and the eps numerator (one fp64) is all-reduced
+(BASELINE.json north_star).  sigma needs one more all-reduce of (sum, nnz).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import torch
+import torch.distributed as dist
+
+from . import engine
+
+
+@dataclass(frozen=True)
+class ShardPlan:
+    n: int            # frames
+    m: int            # filtered size
+    world: int
+    rank: int
+    shard: int        # rows per rank (last rank may own fewer)
+    a0: int           # first owned D2/D3 row
+    a1: int           # one past the last owned row
+    a1h: int          # one past the last computed row (owned + 1 halo row for the P shift)
+    r_lo: int         # first D1 row computed
+    r_hi: int         # one past the last D1 row computed
+
+    @property
+    def padded(self) -> int:
+        return self.shard * self.world
+
+
+def plan_shards(n: int, filter_size: int, stride: int, world: int, rank: int) -> ShardPlan:
+    m = engine.filtered_size(n, filter_size, stride)
+    shard = -(-m // world)
+    a0 = rank * shard
+    a1 = min(m, a0 + shard)
+    if a0 >= m:
+        raise ValueError(f"rank {rank} of {world} would own no rows of the {m} x {m} matrix")
+    a1h = min(m, a1 + 1)
+    return ShardPlan(n, m, world, rank, shard, a0, a1, a1h, a0 * stride, (a1h - 1) * stride + filter_size)
+
+
+def make_exchange(plan: ShardPlan, group=None):
+    """Returns exchange(mvec, eps_buf): in-place all-gather of the per-row minima (each rank wrote
+    its own rows of the padded vector) + all-reduce of the eps numerator."""
+    if plan.world == 1:
+        return None
+    backend = dist.get_backend(group)
+
+    def exchange(mvec: torch.Tensor, eps_buf):
+        mine = mvec[plan.rank * plan.shard:(plan.rank + 1) * plan.shard]
+        if backend == "nccl":
+            dist.all_gather_into_tensor(mvec, mine, group=group)          # in place: NCCL allows it
+        else:
+            chunks = list(mvec.view(plan.world, plan.shard).unbind(0))
+            dist.all_gather(chunks, mine.clone(), group=group)
+        if eps_buf is not None:
+            dist.all_reduce(eps_buf, op=dist.ReduceOp.SUM, group=group)
+
+    return exchange
+
+
+def allreduce_stats(stats: torch.Tensor, group=None) -> torch.Tensor:
+    """(fp64 sum, uint64 nnz) summed over ranks.  The count travels as int64 bits in a second tensor
+    because a fp64 SUM would not add integer bit patterns."""
+    s = stats[:1].clone()
+    z = stats.view(torch.int64)[1:].clone()
+    dist.all_reduce(s, group=group)
+    dist.all_reduce(z, group=group)
+    out = stats.clone()
+    out[:1] = s
+    out.view(torch.int64)[1:] = z
+    return out
+
+
+@dataclass
+class ShardResult:
+    plan: ShardPlan
+    D1: torch.Tensor          # rows [r_lo, r_hi)
+    D2: torch.Tensor          # rows [a0, a1h)
+    D3: torch.Tensor
+    D3_new: torch.Tensor      # rows [a0, a1h)
+    n_sweeps: int
+    eps_trail: list
+    sigma: float | None = None
+    P3: torch.Tensor | None = None        # rows [a0, a1)
+    P3_new: torch.Tensor | None = None
+    counts: torch.Tensor | None = None
+    launches: int = 0
+
+
+def classic_sharded(frames: torch.Tensor, filter_size: int, stride: int, rank: int, world: int,
+                    p: float = 0.7, alpha: float = 0.997, sigma_factor=None, threshold=None, group=None,
+                    packed: engine.PackedFrames | None = None) -> ShardResult:
+    """Distance + filter + converged future cost (+ sigma3 / P3 / P3_new when sigma_factor is given) for
+    this rank's rows.  `frames`: the full [N, ...] uint8 clip on this rank's device."""
+    n = frames.shape[0]
+    plan = plan_shards(n, filter_size, stride, world, rank)
+    pf = engine.pack_frames(frames) if packed is None else packed
+    if not pf.exact_ok:
+        raise engine._lib.AvtexError(f"sharded path needs byte frames inside the Gram domain: {pf.reason}")
+    D1 = engine.gram_l2(pf, plan.r_lo, plan.r_hi - plan.r_lo, symmetric=False)
+    D2, D3 = engine.diag_filter(D1, filter_size, stride, p=p, m=plan.m, a0=plan.a0,
+                                rows_out=plan.a1h - plan.a0, in_row0=plan.r_lo)
+    own = plan.a1 - plan.a0
+    fc = engine.future_cost(D3[:own], alpha, row0=plan.a0, m=plan.m, exchange=make_exchange(plan, group),
+                            pad_to=plan.padded)
+    res = ShardResult(plan, D1, D2, D3, None, fc.n_sweeps, fc.eps_trail)
+    res.launches = 1 + 1 + 1 + fc.passes + 1
+    res.D3_new = engine.future_cost_finalize(D3, fc.mvec, alpha, row0=plan.a0, m=plan.m)
+    if sigma_factor is not None:
+        stats = engine.sum_nnz(res.D3_new[:own])
+        if world > 1:
+            stats = allreduce_stats(stats, group)
+        res.sigma = engine.sigma_from_stats(*engine.read_stats(stats), sigma_factor)
+        res.P3, res.P3_new, res.counts = engine.transition_probs(
+            res.D3_new, res.sigma, shift=1, rows_out=own, threshold=threshold, want_counts=threshold is not None)
+        res.launches += 2
+    return res
+
+
+def gather_survivors(res: ShardResult, group=None):
+    """CSR of P3_new over all ranks, assembled on every rank (the walk runs on rank 0's host)."""
+    rowptr, colidx = engine.csr_from_matrix(res.P3_new, res.counts)
+    if res.plan.world == 1:
+        return rowptr, colidx
+    parts = [None] * res.plan.world
+    dist.all_gather_object(parts, (rowptr, colidx), group=group)
+    import numpy as np
+    counts = np.concatenate([np.diff(rp) for rp, _ in parts])
+    full_ptr = np.concatenate(([0], np.cumsum(counts))).astype(np.int64)
+    return full_ptr, np.concatenate([ci for _, ci in parts])

@@ -1,0 +1,118 @@
+"""GPU parity tests for the contrastive synthesis path (K6/K7) against the golden vectors produced
+by the unmodified ContrastivePredictionTemporal.forward and against the CPU oracle."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from audio_video_textures_b200 import engine
+    assert torch.cuda.is_available()
+    return engine
+
+
+def test_l2_normalize_rows(eng):
+    gen = torch.Generator().manual_seed(0)
+    x = torch.randn(77, 2304, generator=gen)
+    x[5] = 0                                           # zero row: x / max(0, 1e-12) = 0
+    y = eng.l2_normalize_rows(x.cuda()).cpu()
+    np.testing.assert_allclose(y.numpy(), F.normalize(x, dim=1).numpy(), rtol=1e-6, atol=1e-12)
+    assert float(y[5].abs().max()) == 0.0
+
+
+def test_scores_match_reference_forward(eng):
+    from oracle import contrastive as oc
+    g = load_golden("contrastive_small")
+    emb = torch.from_numpy(g["emb"])
+    L = emb.shape[0]
+    tn = eng.l2_normalize_rows(emb.cuda())
+    for q, key in ((10, "ref_logits_q10"), (L - 1, "ref_logits_qlast")):
+        o = eng.cosine_scores(tn, tn[q], float(g["temp"])).cpu()
+        ids = oc.target_order(q, L)
+        np.testing.assert_allclose(o[ids].numpy(), g[key], rtol=1e-5, atol=2e-6)
+
+
+def test_similarity_tail_matches_oracle_chunk(eng):
+    from audio_video_textures_b200.contrastive.models import ContrastivePredictionTemporal, similarity_tail
+    from oracle import contrastive as oc
+    gen = torch.Generator().manual_seed(1)
+    q = torch.randn(3, 200, generator=gen)
+    t = torch.randn(3, 17, 200, generator=gen)
+    want = oc.similarity_chunk(q, t, 0.07)
+    got = similarity_tail(q.cuda(), t.cuda(), 0.07).cpu()
+    np.testing.assert_allclose(got.numpy(), want.numpy(), rtol=1e-5, atol=2e-6)
+    # model_type 2 + driving audio through the class (embedding boundary)
+    qa, ta, da = torch.rand(3, 24, generator=gen), torch.rand(3, 17, 24, generator=gen), torch.rand(3, 24, generator=gen)
+    m = ContrastivePredictionTemporal(model_type=2, temp=0.1)
+    out, out_a = m(q.cuda(), t.cuda(), q_audio_eg=qa.cuda(), t_audio_eg=ta.cuda(), driving_audio=da.cuda())
+    want = oc.similarity_chunk(torch.cat((q, qa), 1), torch.cat((t, ta), 2), 0.1)
+    want_a = oc.audio_chunk(da, ta, 0.1)
+    np.testing.assert_allclose(out.cpu().numpy(), want.numpy(), rtol=1e-5, atol=2e-6)
+    np.testing.assert_allclose(out_a.cpu().numpy(), want_a.numpy(), rtol=1e-5, atol=2e-6)
+
+
+@pytest.mark.parametrize("L,q", [(96, 10), (96, 95), (96, 0), (96, 94), (5000, 1234), (2, 0), (2, 1), (1025, 1024)])
+@pytest.mark.parametrize("audio", [False, True])
+def test_select_step_matches_oracle(eng, L, q, audio):
+    """Same logits on both sides -> same survivor list (bit-exact), values rtol 1e-5."""
+    from oracle import contrastive as oc
+    gen = torch.Generator().manual_seed(L * 7 + q)
+    o_nat = torch.randn(L, generator=gen) * 2 + 6          # logits in natural window order
+    a_nat = torch.rand(L, generator=gen) * 9 + 0.5 if audio else None
+    th, alpha = 0.3, 0.5
+    ids = oc.target_order(q, L)
+    out, choices, mixed = oc.mix_and_select(o_nat[ids], a_nat[ids] if audio else None, alpha, th)
+    if oc.select_margin(mixed, th) < 1e-5:
+        pytest.skip("fixture too close to the threshold cut")
+    sel = torch.zeros(L + 1, dtype=torch.int32, device="cuda")
+    vals = torch.zeros(L, device="cuda")
+    eng.select_step(o_nat.cuda(), a_nat.cuda() if audio else None, q, alpha, th, sel[1:], sel[:1], vals)
+    n = int(sel[0])
+    got = sel[1:n + 1].cpu().numpy()
+    np.testing.assert_array_equal(got, ids[choices.numpy()])
+    np.testing.assert_allclose(vals.cpu()[ids].numpy(), out.numpy(), rtol=1e-5, atol=0)
+
+
+def test_synthesis_sequences_bit_exact(eng):
+    from audio_video_textures_b200.contrastive.validate import start_segment, synthesize
+    g = load_golden("contrastive_small")
+    emb = torch.from_numpy(g["emb"]).cuda()
+    kw = dict(temp=float(g["temp"]), threshold=float(g["th"]), fps=int(g["fps"]), new_video_length=int(g["nvl"]),
+              window=int(g["window"]), stride=int(g["stride"]), mini_batchsize=int(g["mbs"]))
+    np.random.seed(int(g["seed"]))
+    r = synthesize(emb, q_start=10, **kw)
+    np.testing.assert_array_equal(r["q_ids"], g["synth_q_ids"])
+    np.testing.assert_array_equal(r["frame_ids"], g["synth_frame_ids"])
+    np.testing.assert_array_equal(r["nz_counts"], g["synth_nz"])
+    assert r["jump_count"] == int(g["synth_jumps"])
+    qa, das, dad = (torch.from_numpy(g[k]).cuda() for k in ("q_audio", "da_source", "da_driving"))
+    assert start_segment(das, dad[0]) == int(g["audio_start"])
+    np.random.seed(int(g["seed"]))
+    r2 = synthesize(emb, alpha=0.5, q_audio=qa, da_source=das, da_driving=dad, **kw)
+    assert r2["start"] == int(g["audio_start"])
+    np.testing.assert_array_equal(r2["q_ids"], g["synth2_q_ids"])
+    np.testing.assert_array_equal(r2["frame_ids"], g["synth2_frame_ids"])
+    np.testing.assert_array_equal(r2["nz_counts"], g["synth2_nz"])
+
+
+def test_synthesis_medium_against_oracle(eng):
+    """L = 3000, D = 256: the CUDA loop and the CPU oracle choose the same windows under one seed."""
+    from audio_video_textures_b200.contrastive.validate import synthesize
+    from audio_video_textures_b200.synth import synth_embeddings
+    from oracle import contrastive as oc
+    emb = synth_embeddings(3000, 256, seed=3)
+    np.random.seed(11)
+    want = oc.synthesize(emb, 0.1, 0.3, 150, 30, 10, 15, 6, q_start=10, return_debug=True)
+    if min(want["margins"]) < 1e-5:
+        pytest.skip("fixture too close to the threshold cut")
+    np.random.seed(11)
+    got = synthesize(emb.cuda(), temp=0.1, threshold=0.3, fps=30, new_video_length=10, window=15, stride=6,
+                     q_start=10)
+    assert got["q_ids"] == want["q_ids"] and got["frame_ids"] == want["frame_ids"]
+    assert got["jump_count"] == want["jump_count"] and got["nz_counts"] == want["nz_counts"]
