@@ -17,11 +17,22 @@ extern "C" int avtex_abi_version(void) { return AVTEX_ABI_VERSION; }
 
 extern "C" const char *avtex_last_error(void) { return g_err; }
 
+// cudaGetDeviceProperties costs milliseconds; the three attributes needed are cached per device.
 extern "C" int avtex_device_info(int device, int *sm_count, int *cc) {
-    cudaDeviceProp prop;
-    AVTEX_CUDA(cudaGetDeviceProperties(&prop, device));
-    if (sm_count) *sm_count = prop.multiProcessorCount;
-    if (cc) *cc = prop.major * 10 + prop.minor;
+    static int cached_sms[64], cached_cc[64];
+    static bool have[64] = {false};
+    AVTEX_REQUIRE(device >= 0 && device < 64, "device_info: device index %d out of range", device);
+    if (!have[device]) {
+        int sms = 0, major = 0, minor = 0;
+        AVTEX_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+        AVTEX_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device));
+        AVTEX_CUDA(cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, device));
+        cached_sms[device] = sms;
+        cached_cc[device] = major * 10 + minor;
+        have[device] = true;
+    }
+    if (sm_count) *sm_count = cached_sms[device];
+    if (cc) *cc = cached_cc[device];
     return 0;
 }
 

@@ -1,0 +1,210 @@
+"""CPU tests (no GPU): the C-ABI library loads and exports every declared symbol, host-side logic
+(tile schedule, shard plan, sigma arithmetic, walk over survivor lists, argument surfaces) and the
+N>1 exchange over gloo with world_size 2."""
+import os
+import re
+import socket
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT, load_golden
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "avtex.h")).read()
+    return sorted(set(re.findall(r"AVTEX_API\s+[\w\s\*]+?\b(avtex_\w+)\s*\(", text)))
+
+
+def test_cabi_library_exports_every_declared_symbol():
+    import ctypes
+    from audio_video_textures_b200 import _lib
+    lib = _lib.load()
+    names = _declared_symbols()
+    assert len(names) >= 20
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/avtex.h but not exported"
+    assert set(_lib.SIGNATURES) | {"avtex_last_error"} == set(names)
+    assert lib.avtex_abi_version() == _lib.ABI_VERSION
+    assert isinstance(lib.avtex_last_error(), bytes)
+    assert isinstance(ctypes.CDLL(_lib.LIB_PATH), ctypes.CDLL)
+
+
+def test_product_path_has_no_cpu_fallback():
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from audio_video_textures_b200.classic.computeD1 import compute_D1
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        compute_D1(torch.zeros(4, 2, 2, 3), 4.5, "RGB")
+    import audio_video_textures_b200 as pkg
+    src_dir = os.path.dirname(pkg.__file__)
+    for dirpath, _, files in os.walk(src_dir):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in src and "from oracle" not in src, f"{f} imports the oracle"
+
+
+@pytest.mark.parametrize("TM,TN", [(1, 1), (2, 1), (5, 3), (16, 8), (17, 9), (40, 20), (98, 391), (782, 391)])
+def test_gram_tile_schedule_symmetric_covers_upper_triangle_once(TM, TN):
+    from audio_video_textures_b200 import engine
+    if TM > 2 * TN:
+        pytest.skip("not a square matrix tiling")
+    s = engine.gram_tile_schedule(TM, TN, True)
+    need = {(tm, tn) for tm in range(TM) for tn in range(TN) if tn * 256 + 255 >= tm * 128}
+    assert len(s) == len(set(s)) and set(s) == need
+
+
+@pytest.mark.parametrize("TM,TN", [(1, 1), (3, 7), (8, 2), (9, 2), (98, 391)])
+def test_gram_tile_schedule_rowblock_covers_all_once(TM, TN):
+    from audio_video_textures_b200 import engine
+    s = engine.gram_tile_schedule(TM, TN, False)
+    assert sorted(s) == [(a, b) for a in range(TM) for b in range(TN)]
+    # groups of 8 row tiles, column-major inside a group (L2 footprint of a wave)
+    assert s[:min(8, TM)] == [(i, 0) for i in range(min(8, TM))]
+
+
+def test_binomial_taps_and_sigma_arithmetic():
+    from audio_video_textures_b200 import engine
+    from oracle import classic
+    for fs in (1, 2, 8, 16, 40, 64):
+        np.testing.assert_array_equal(engine.binomial_taps(fs), classic.binomial_weights(fs).numpy())
+    g = torch.Generator().manual_seed(0)
+    D = torch.rand(300, 300, generator=g) * 1e4
+    D.fill_diagonal_(0)
+    f = torch.tensor(4.52, dtype=torch.float32)
+    nnz = torch.nonzero(D).size(0)
+    want = f * (D.sum() / nnz)
+    got = engine.sigma_from_stats(float(D.double().sum()), nnz, f)
+    np.testing.assert_allclose(got, want.item(), rtol=1e-6)
+    assert isinstance(got, np.float32)
+    assert engine.filtered_size(5000, 40, 4) == 1241 and engine.filtered_size(300, 40, 1) == 261
+
+
+@pytest.mark.parametrize("name", ["classic_small_m1", "classic_ragged_m2", "classic_stride_m3"])
+def test_walk_over_survivor_lists_matches_golden(name):
+    """texture_walk consumes (rowptr, colidx) -- exactly what the GPU compaction returns."""
+    from audio_video_textures_b200.classic.video_textures import texture_walk
+    g = load_golden(name)
+    np.random.seed(int(g["seed"]))
+    frames, jumps = texture_walk((g["ref_P3new_rowptr"], g["ref_P3new_cols"]), int(g["model_type"]),
+                                 int(g["fps"]), int(g["nvl"]), int(g["stride"]), int(g["fs"]))
+    np.testing.assert_array_equal(np.array(frames), g["walk_frames"])
+    assert jumps == int(g["walk_jump_count"])
+
+
+def test_argument_surfaces_match_reference_defaults():
+    from audio_video_textures_b200.classic.video_textures import build_parser as classic_parser
+    from audio_video_textures_b200.contrastive.main import build_parser as cvt_parser
+    a = classic_parser().parse_args([])
+    assert (a.model_type, a.feats, a.filter_size, a.batch_size, a.stride, a.new_video_length, a.threshold,
+            a.fps, a.sr, a.SF, a.slow, a.interpolation) == (1, "RGB", 40, 64, 4, 30, 0.08, 30, 22050, 3, False, True)
+    a = classic_parser().parse_args("-m 3 -bs 48 -fs 16 -stride 2 -t 0.1 -s -nvl 10".split())
+    assert (a.model_type, a.batch_size, a.filter_size, a.stride, a.threshold, a.slow, a.new_video_length) == \
+        (3, 48, 16, 2, 0.1, True, 10)
+    c = cvt_parser().parse_args([])
+    assert (c.model_type, c.temp, c.threshold, c.alpha, c.mini_batchsize, c.window, c.stride,
+            c.new_video_length, c.evaluate, c.da_feats) == (1, 0.1, 0.0, 0.5, 150, 20, 4, 30, False, "VGG")
+    c = cvt_parser().parse_args("-e -th 0.3 -temp 0.1 -alpha 0.5 -mbs 100 -m 2".split())
+    assert (c.evaluate, c.threshold, c.temp, c.alpha, c.mini_batchsize, c.model_type) == (True, 0.3, 0.1, 0.5, 100, 2)
+
+
+@pytest.mark.parametrize("n,fs,stride,world", [(5000, 40, 4, 8), (300, 40, 1, 2), (100000, 40, 4, 8), (520, 40, 4, 3)])
+def test_shard_plan_covers_rows_and_halos(n, fs, stride, world):
+    from audio_video_textures_b200 import dist as avd
+    from audio_video_textures_b200 import engine
+    m = engine.filtered_size(n, fs, stride)
+    owned = []
+    for r in range(world):
+        p = avd.plan_shards(n, fs, stride, world, r)
+        assert p.m == m and p.a0 == r * p.shard and p.a0 < p.a1 <= m
+        assert p.a1h == min(m, p.a1 + 1)                              # one halo row for the P shift
+        assert p.r_lo == p.a0 * stride and p.r_hi == (p.a1h - 1) * stride + fs <= n
+        assert p.padded >= m and p.padded % world == 0
+        owned.extend(range(p.a0, p.a1))
+    assert owned == list(range(m))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _gloo_worker(rank, world, port, D3_np, alpha, out_dir):
+    """Emulates the sharded future-cost loop of dist.classic_sharded with torch-CPU arithmetic in
+    place of the kernels (test only) and the REAL exchange / stats all-reduce over gloo."""
+    import torch.distributed as dist
+    from audio_video_textures_b200 import dist as avd
+    from audio_video_textures_b200 import engine
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    D3 = torch.from_numpy(D3_np)
+    M = D3.shape[0]
+    shard = -(-M // world)
+    plan = avd.ShardPlan(0, M, world, rank, shard, rank * shard, min(M, (rank + 1) * shard),
+                         min(M, (rank + 1) * shard + 1), 0, 0)
+    exchange = avd.make_exchange(plan)
+    rows = D3[plan.a0:plan.a1]
+    a32 = torch.tensor(alpha, dtype=torch.float32)
+
+    def sweep(prev, prev2, out, eps):
+        X = rows if prev is None else rows + a32 * prev[:M]
+        if prev is not None and plan.a0 == 0:
+            X = X.clone(); X[0] = rows[0]
+        Y = X.clone()
+        idx = torch.arange(plan.a0, plan.a1)
+        Y[idx - plan.a0, idx] = float("inf")
+        out[plan.a0:plan.a1] = Y.min(1)[0]
+        if eps is not None:
+            Xp = rows if prev2 is None else rows + a32 * prev2[:M]
+            if plan.a0 == 0:
+                Xp = Xp.clone(); Xp[0] = rows[0]
+            eps += ((X - Xp) ** 2).double().sum()
+
+    bufs = [torch.zeros(plan.padded) for _ in range(3)]
+    eps = torch.zeros(1, dtype=torch.float64)
+    sweep(None, None, bufs[0], None)
+    exchange(bufs[0], None)
+    cur, prev2, free, n_sweeps = bufs[0], None, [bufs[1], bufs[2]], 0
+    for p in range(1, 100):
+        out = free.pop()
+        eps.zero_()
+        sweep(cur, prev2, out, eps)
+        exchange(out, eps)
+        e = np.float32(eps.item() / (M * M))
+        if not (e > np.float32(engine.F32_EPS_STOP)):
+            n_sweeps = p
+            break
+        if prev2 is not None:
+            free.append(prev2)
+        prev2, cur = cur, out
+    D3_new = rows + a32 * cur[:M]
+    if plan.a0 == 0:
+        D3_new[0] = rows[0]
+    stats = torch.zeros(2, dtype=torch.float64)
+    stats[0] = D3_new.double().sum()
+    stats.view(torch.int64)[1] = int((D3_new != 0).sum())
+    tot = avd.allreduce_stats(stats)
+    np.savez(os.path.join(out_dir, f"r{rank}.npz"), D3_new=D3_new.numpy(), n_sweeps=n_sweeps,
+             total=float(tot[0]), nnz=int(tot.view(torch.int64)[1]), a0=plan.a0)
+    dist.destroy_process_group()
+
+
+def test_row_sharded_future_cost_exchange_gloo_world2(tmp_path):
+    import torch.multiprocessing as mp
+    from oracle import classic
+    g = load_golden("classic_small_m1")
+    D3 = torch.from_numpy(g["ref_D2"]) ** 0.7
+    want, trail = classic.future_cost(D3)
+    port = _free_port()
+    mp.spawn(_gloo_worker, args=(2, port, D3.numpy(), 0.997, str(tmp_path)), nprocs=2, join=True)
+    parts = [np.load(tmp_path / f"r{r}.npz") for r in range(2)]
+    got = np.concatenate([p["D3_new"] for p in parts])
+    np.testing.assert_array_equal(got, want.numpy())                  # sharded == single process, bit for bit
+    assert all(int(p["n_sweeps"]) == len(trail) for p in parts)
+    np.testing.assert_allclose(parts[0]["total"], want.double().sum().item(), rtol=1e-12)
+    assert int(parts[0]["nnz"]) == int((want != 0).sum()) == int(parts[1]["nnz"])
