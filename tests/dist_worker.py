@@ -1,0 +1,58 @@
+"""torchrun worker for tests/test_gpu_dist.py: row-sharded classic++ vs the single-GPU result."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from audio_video_textures_b200 import dist as avd  # noqa: E402
+from audio_video_textures_b200 import engine  # noqa: E402
+from audio_video_textures_b200.classic.video_textures import texture_walk  # noqa: E402
+from audio_video_textures_b200.synth import synth_video  # noqa: E402
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    n, h, w, fs, stride, th, f = (int(v) for v in sys.argv[1:6]) + (0.08, 4.5)
+    frames = synth_video(n, h, w, seed=2).cuda()
+    res = avd.classic_sharded(frames, fs, stride, rank, world, sigma_factor=f, threshold=th)
+    rowptr, colidx = avd.gather_survivors(res)
+    # single-GPU result on every rank
+    pf = engine.pack_frames(frames)
+    D1 = engine.gram_l2(pf)
+    D2, D3 = engine.diag_filter(D1, fs, stride, p=0.7)
+    fc = engine.future_cost(D3)
+    stats = engine.new_stats(frames.device)
+    D3n = engine.future_cost_finalize(D3, fc.mvec, stats=stats)
+    sigma = engine.sigma_from_stats(*engine.read_stats(stats), f)
+    P3, P3n, counts = engine.transition_probs(D3n, sigma, threshold=th, want_counts=True)
+    rp1, ci1 = engine.csr_from_matrix(P3n, counts)
+    p = res.plan
+    own = p.a1 - p.a0
+    ok = dict(
+        D1=torch.equal(res.D1, D1[p.r_lo:p.r_hi]), D2=torch.equal(res.D2, D2[p.a0:p.a1h]),
+        D3n=torch.equal(res.D3_new, D3n[p.a0:p.a1h]), sweeps=res.n_sweeps == fc.n_sweeps,
+        sigma=abs(float(res.sigma) - float(sigma)) <= 1e-6 * float(sigma),
+        P3=torch.allclose(res.P3, P3[p.a0:p.a1], rtol=1e-5, atol=0),
+        csr=np.array_equal(rowptr, rp1) and np.array_equal(colidx, ci1))
+    np.random.seed(0)
+    a = texture_walk((rowptr, colidx), 1, 30, 5, stride, fs)
+    np.random.seed(0)
+    b = texture_walk((rp1, ci1), 1, 30, 5, stride, fs)
+    ok["walk"] = a == b
+    flag = torch.tensor([int(all(ok.values()))], device="cuda")
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        print("DIST_CHECK", "PASS" if int(flag) == 1 else "FAIL", ok, "world", world, "M", p.m, "sweeps", res.n_sweeps)
+    else:
+        if not all(ok.values()):
+            print("rank", rank, ok)
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
