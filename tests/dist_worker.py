@@ -17,7 +17,8 @@ def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    n, h, w, fs, stride, th, f = (int(v) for v in sys.argv[1:6]) + (0.08, 4.5)
+    n, h, w, fs, stride = (int(v) for v in sys.argv[1:6])
+    th, f = 0.08, 4.5
     frames = synth_video(n, h, w, seed=2).cuda()
     res = avd.classic_sharded(frames, fs, stride, rank, world, sigma_factor=f, threshold=th)
     rowptr, colidx = avd.gather_survivors(res)
