@@ -40,6 +40,7 @@ SIGNATURES = {
     "avtex_select_step": [_p, _p, _i64, _i64, _f32, _f32, _f32, _p, _p, _p, _int, _p],
     "avtex_audio_start": [_p, _i64, _i64, _i64, _p, _p, _p, _int, _p],
     "avtex_gram_tile_schedule": [_int, _int, _int, C.POINTER(_int), C.POINTER(_int), _int],
+    "avtex_gram_tile_schedule2": [_int, _int, _int, C.POINTER(_int), C.POINTER(_int), _int],
 }
 
 _lib = None

@@ -16,7 +16,8 @@ def compute_D2(D1: torch.Tensor, sigma_factor: float, filter_size: int = 16, str
     """
     if not D1.is_cuda:
         D1 = D1.cuda()
-    D1 = D1.contiguous()
+    if D1.stride(-1) != 1:
+        D1 = D1.contiguous()
     taps = engine.binomial_taps(filter_size)
     stats = engine.new_stats(D1.device)
     D2, _ = engine.diag_filter(D1, filter_size, stride, stats=stats, taps=taps)

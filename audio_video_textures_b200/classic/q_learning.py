@@ -23,7 +23,8 @@ def q_learning(
     """
     if not D2.is_cuda:
         D2 = D2.cuda()
-    D2 = D2.contiguous()
+    if D2.stride(-1) != 1:
+        D2 = D2.contiguous()
     # D3 = D2 ** p through the filter kernel's fused pow with the identity tap (fs = 1, stride 1)
     _, D3 = engine.diag_filter(D2, 1, 1, p=p, taps=[1.0])
     fc = engine.future_cost(D3, alpha, verbose=True)

@@ -4,7 +4,7 @@
 // HBM-bound: reads 4 N^2 B (every D1 row is touched), writes 4 M^2 (+4 M^2) B.
 //
 // The reference runs a dense fs x fs cuDNN convolution whose kernel is 97.5 % zeros.  Here one thread
-// walks ONE input diagonal and keeps R consecutive outputs of that diagonal in registers, so it
+// walks ONE input diagonal and keeps R (16 at stride 1, 8 otherwise) consecutive outputs of that diagonal in registers, so it
 // issues (R-1)*s + fs loads for R outputs instead of R*fs, and the taps are compile-time indexed
 // kernel parameters (constant-bank FFMA operands: no shared-memory or LDS traffic at all).  Within
 // a warp consecutive threads own consecutive diagonals, so every load is a coalesced row segment.
@@ -13,54 +13,79 @@
 namespace {
 
 constexpr int FT = 128;      // threads per CTA = diagonals per CTA
-constexpr int FR = 8;        // outputs per thread along its diagonal
 
 struct Taps64 { float w[64]; };
 struct TapsBig { float w[960]; };
 
-template <int FS, int S>
+// Out-of-line so the 8/16 calls per thread do not multiply the (already fully unrolled) code size:
+// the first version stalled on instruction fetch (ncu: stalled_no_instruction was the top reason).
+__device__ __noinline__ float pow_pos_call(float x, float p) { return pow_pos(x, p); }
+
+template <int FS, int S, int FR>
 __global__ void __launch_bounds__(FT)
 diag_filter_kernel(const float *__restrict__ D1, int64_t ld1, int64_t in_row0, int64_t in_rows, const Taps64 taps,
                    int64_t a0, int64_t rows_out, int64_t m, float *__restrict__ D2, int64_t ld2,
                    float *__restrict__ D3, int64_t ld3, float p, double *sum, unsigned long long *nnz) {
     __shared__ double sred[32];
     __shared__ unsigned long long nred[32];
+    constexpr int T = (FR - 1) * S + FS;
     const int64_t n_in = (m - 1) * S + FS;                                  // valid input rows / cols
     const int64_t a_base = a0 + int64_t(blockIdx.y) * FR;                   // first output row of the band
-    const int64_t b0 = int64_t(blockIdx.x) * FT + threadIdx.x - (FR - 1);   // output col of output 0
+    const int64_t b_blk = int64_t(blockIdx.x) * FT - (FR - 1);              // output col of thread 0's output 0
+    const int64_t b0 = b_blk + threadIdx.x;
     const int64_t grow = a_base * S;                                        // global input row at t = 0
     const int64_t gcol = b0 * S;
     const float *src = D1 + (grow - in_row0) * ld1 + gcol;
+    const int64_t step = ld1 + 1;
     float acc[FR];
 #pragma unroll
     for (int i = 0; i < FR; ++i) acc[i] = 0.f;
-    constexpr int T = (FR - 1) * S + FS;
+    // CTA-uniform: every load of every thread is in range -> no per-load predicates (all CTAs except
+    // those on the matrix border)
+    const bool interior = (b_blk * S >= 0) && ((b_blk + FT - 1) * S + T - 1 < n_in) &&
+                          (grow + T - 1 < in_row0 + in_rows) && (grow + T - 1 < n_in);
+    if (interior) {
 #pragma unroll
-    for (int t = 0; t < T; ++t) {
-        const bool ok = (gcol + t >= 0) && (gcol + t < n_in) && (grow + t < in_row0 + in_rows);
-        const float x = ok ? __ldg(src + int64_t(t) * (ld1 + 1)) : 0.f;
+        for (int t = 0; t < T; ++t) {
+            const float x = __ldg(src);
+            src += step;
 #pragma unroll
-        for (int i = 0; i < FR; ++i) {
-            const int kk = t - i * S;
-            if (kk >= 0 && kk < FS) acc[i] = fmaf(taps.w[kk], x, acc[i]);
+            for (int i = 0; i < FR; ++i) {
+                const int kk = t - i * S;
+                if (kk >= 0 && kk < FS) acc[i] = fmaf(taps.w[kk], x, acc[i]);
+            }
+        }
+    } else {
+#pragma unroll
+        for (int t = 0; t < T; ++t) {
+            const bool ok = (gcol + t >= 0) && (gcol + t < n_in) && (grow + t < in_row0 + in_rows);
+            const float x = ok ? __ldg(src) : 0.f;
+            src += step;
+#pragma unroll
+            for (int i = 0; i < FR; ++i) {
+                const int kk = t - i * S;
+                if (kk >= 0 && kk < FS) acc[i] = fmaf(taps.w[kk], x, acc[i]);
+            }
         }
     }
     double s = 0.0;
-    unsigned long long z = 0;
+    int z = 0;
+    float *o2 = D2 + (a_base - a0) * ld2 + b0;
+    float *o3 = (D3 != nullptr) ? D3 + (a_base - a0) * ld3 + b0 : nullptr;
 #pragma unroll
     for (int i = 0; i < FR; ++i) {
         const int64_t a = a_base + i, b = b0 + i;
         if (a < a0 + rows_out && b >= 0 && b < m) {
-            D2[(a - a0) * ld2 + b] = acc[i];
-            if (D3 != nullptr) D3[(a - a0) * ld3 + b] = powf(acc[i], p);
-            s += acc[i];
+            o2[i * (ld2 + 1)] = acc[i];
+            if (o3 != nullptr) o3[i * (ld3 + 1)] = pow_pos_call(acc[i], p);
+            s += (double)acc[i];
             z += (acc[i] != 0.f);
         }
     }
     if (sum != nullptr) {
-        s = block_reduce(s, 0.0, OpAdd<double>(), sred);
-        z = block_reduce(z, 0ull, OpAdd<unsigned long long>(), nred);
-        if (threadIdx.x == 0) { atomicAdd(sum, s); atomicAdd(nnz, z); }
+        const double sd = block_reduce(s, 0.0, OpAdd<double>(), sred);
+        const unsigned long long zd = block_reduce((unsigned long long)z, 0ull, OpAdd<unsigned long long>(), nred);
+        if (threadIdx.x == 0) { atomicAdd(sum, sd); atomicAdd(nnz, zd); }
     }
 }
 
@@ -81,7 +106,7 @@ diag_filter_generic_kernel(const float *__restrict__ D1, int64_t ld1, int64_t in
         float acc = 0.f;
         for (int k = 0; k < fs; ++k) acc = fmaf(taps.w[k], __ldg(src + int64_t(k) * (ld1 + 1)), acc);
         D2[(a - a0) * ld2 + b] = acc;
-        if (D3 != nullptr) D3[(a - a0) * ld3 + b] = powf(acc, p);
+        if (D3 != nullptr) D3[(a - a0) * ld3 + b] = pow_pos(acc, p);
         s = acc;
         z = (acc != 0.f);
     }
@@ -92,14 +117,18 @@ diag_filter_generic_kernel(const float *__restrict__ D1, int64_t ld1, int64_t in
     }
 }
 
+// outputs per thread along its diagonal: (FR-1)*S+FS loads serve FR outputs
+template <int S> constexpr int filter_r() { return S == 1 ? 16 : 8; }
+
 template <int FS, int S>
 void launch_fast(const float *D1, int64_t ld1, int64_t in_row0, int64_t in_rows, const float *h_w, int64_t a0,
                  int64_t rows_out, int64_t m, float *D2, int64_t ld2, float *D3, int64_t ld3, float p,
                  double *sum, unsigned long long *nnz, cudaStream_t st) {
     Taps64 taps;
     for (int i = 0; i < 64; ++i) taps.w[i] = (i < FS) ? h_w[i] : 0.f;
+    constexpr int FR = filter_r<S>();
     dim3 grid((unsigned)((m + FR - 1 + FT - 1) / FT), (unsigned)((rows_out + FR - 1) / FR));
-    diag_filter_kernel<FS, S><<<grid, FT, 0, st>>>(D1, ld1, in_row0, in_rows, taps, a0, rows_out, m, D2, ld2, D3,
+    diag_filter_kernel<FS, S, FR><<<grid, FT, 0, st>>>(D1, ld1, in_row0, in_rows, taps, a0, rows_out, m, D2, ld2, D3,
                                                    ld3, p, sum, nnz);
 }
 
@@ -125,7 +154,7 @@ extern "C" int avtex_diag_filter_pow(const float *D1, int64_t ld1, int64_t in_ro
     const int key = fs * 100 + stride;
 #define AVTEX_FAST(FS_, S_)                                                                            \
     case FS_ * 100 + S_:                                                                               \
-        AVTEX_REQUIRE((rows_out + FR - 1) / FR <= 65535, "diag_filter: too many row bands");           \
+        AVTEX_REQUIRE((rows_out + filter_r<S_>() - 1) / filter_r<S_>() <= 65535, "diag_filter: too many row bands"); \
         launch_fast<FS_, S_>(D1, ld1, in_row0, in_rows, h_w, a0, rows_out, m, D2, ld2, D3, ld3, p, sum, nnz, st); \
         break;
     switch (key) {

@@ -12,6 +12,7 @@
 // fl(alpha*m) and the add are written with __fmul_rn / __fadd_rn: nvcc must not contract them into
 // an FMA, the reference rounds twice (`alpha * mins`, then `D3[i] + ...`).
 #include <float.h>
+#include <math.h>
 
 #include "common.cuh"
 
@@ -24,16 +25,53 @@ struct SweepAcc {
     double e;
 };
 
-__device__ __forceinline__ void sweep_elem(float v, int64_t k, int64_t j, bool use_a, bool do_eps,
-                                           const float *mp, const float *mp2, float alpha, SweepAcc &acc) {
+// One element: x = D3 + fl(alpha*m_prev); row minimum off the diagonal; eps numerator against
+// x_prev = D3 + fl(alpha*m_prev2).  a / a2 are the already loaded m_prev[k] / m_prev2[k].
+template <bool USE_A, bool EPS, bool HAVE2>
+__device__ __forceinline__ void sweep_elem(float v, float a, float a2, int64_t k, int64_t j, float alpha,
+                                           SweepAcc &acc) {
     float x = v;
-    if (use_a) x = __fadd_rn(v, __fmul_rn(alpha, mp[k]));
+    if (USE_A) x = __fadd_rn(v, __fmul_rn(alpha, a));
     if (k != j) acc.mn = fminf(acc.mn, x);
-    if (do_eps) {
-        const float xp = (mp2 != nullptr) ? __fadd_rn(v, __fmul_rn(alpha, mp2[k])) : v;
+    if (EPS) {
+        const float xp = HAVE2 ? __fadd_rn(v, __fmul_rn(alpha, a2)) : v;
         const float d = __fsub_rn(x, xp);
         acc.e += (double)__fmul_rn(d, d);
     }
+}
+
+template <bool USE_A, bool EPS, bool HAVE2>
+__device__ __forceinline__ void sweep_vec4(const float4 v, const float *__restrict__ mp,
+                                           const float *__restrict__ mp2, int64_t k, int64_t j, float alpha,
+                                           SweepAcc &acc) {
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), a2 = a;
+    if (USE_A) a = *reinterpret_cast<const float4 *>(mp + k);
+    if (EPS && HAVE2) a2 = *reinterpret_cast<const float4 *>(mp2 + k);
+    sweep_elem<USE_A, EPS, HAVE2>(v.x, a.x, a2.x, k + 0, j, alpha, acc);
+    sweep_elem<USE_A, EPS, HAVE2>(v.y, a.y, a2.y, k + 1, j, alpha, acc);
+    sweep_elem<USE_A, EPS, HAVE2>(v.z, a.z, a2.z, k + 2, j, alpha, acc);
+    sweep_elem<USE_A, EPS, HAVE2>(v.w, a.w, a2.w, k + 3, j, alpha, acc);
+}
+
+template <bool USE_A, bool EPS, bool HAVE2>
+__device__ __forceinline__ void sweep_row(const float *__restrict__ row, int64_t m, int64_t j,
+                                          const float *__restrict__ mp, const float *__restrict__ mp2,
+                                          float alpha, SweepAcc &acc) {
+    const bool vec = ((reinterpret_cast<uintptr_t>(row) & 15) == 0);
+    const int64_t mv = vec ? (m & ~int64_t(3)) : 0;
+    int64_t k = int64_t(threadIdx.x) * 4;
+    // four independent 128-bit streaming loads in flight per thread (HBM latency hiding)
+    for (; k + 3 * ST * 4 < mv; k += 4 * ST * 4) {
+        const float4 v0 = ld_stream_f4(row + k), v1 = ld_stream_f4(row + k + ST * 4),
+                     v2 = ld_stream_f4(row + k + 2 * ST * 4), v3 = ld_stream_f4(row + k + 3 * ST * 4);
+        sweep_vec4<USE_A, EPS, HAVE2>(v0, mp, mp2, k, j, alpha, acc);
+        sweep_vec4<USE_A, EPS, HAVE2>(v1, mp, mp2, k + ST * 4, j, alpha, acc);
+        sweep_vec4<USE_A, EPS, HAVE2>(v2, mp, mp2, k + 2 * ST * 4, j, alpha, acc);
+        sweep_vec4<USE_A, EPS, HAVE2>(v3, mp, mp2, k + 3 * ST * 4, j, alpha, acc);
+    }
+    for (; k < mv; k += ST * 4) sweep_vec4<USE_A, EPS, HAVE2>(ld_stream_f4(row + k), mp, mp2, k, j, alpha, acc);
+    for (int64_t s = mv + threadIdx.x; s < m; s += ST)
+        sweep_elem<USE_A, EPS, HAVE2>(row[s], USE_A ? mp[s] : 0.f, (EPS && HAVE2) ? mp2[s] : 0.f, s, j, alpha, acc);
 }
 
 __global__ void __launch_bounds__(ST)
@@ -44,21 +82,13 @@ future_cost_sweep_kernel(const float *__restrict__ D3, int64_t ld, int64_t row0,
     __shared__ double dred[32];
     const int64_t j = row0 + blockIdx.x;
     const float *row = D3 + int64_t(blockIdx.x) * ld;
-    const bool use_a = (mp != nullptr) && (j >= 1);
+    const bool use_a = (mp != nullptr) && (j >= 1);          // row 0 is never updated (q_learning.py:42)
     const bool do_eps = (eps_sum != nullptr) && use_a;
-    SweepAcc acc{FLT_MAX, 0.0};
-    acc.mn = INFINITY;
-    const bool vec = ((reinterpret_cast<uintptr_t>(row) & 15) == 0);
-    const int64_t mv = vec ? (m & ~int64_t(3)) : 0;
-    for (int64_t k = int64_t(threadIdx.x) * 4; k < mv; k += ST * 4) {
-        const float4 v = ld_stream_f4(row + k);
-        sweep_elem(v.x, k + 0, j, use_a, do_eps, mp, mp2, alpha, acc);
-        sweep_elem(v.y, k + 1, j, use_a, do_eps, mp, mp2, alpha, acc);
-        sweep_elem(v.z, k + 2, j, use_a, do_eps, mp, mp2, alpha, acc);
-        sweep_elem(v.w, k + 3, j, use_a, do_eps, mp, mp2, alpha, acc);
-    }
-    for (int64_t k = mv + threadIdx.x; k < m; k += ST)
-        sweep_elem(row[k], k, j, use_a, do_eps, mp, mp2, alpha, acc);
+    SweepAcc acc{INFINITY, 0.0};
+    if (!use_a) sweep_row<false, false, false>(row, m, j, mp, mp2, alpha, acc);
+    else if (!do_eps) sweep_row<true, false, false>(row, m, j, mp, mp2, alpha, acc);
+    else if (mp2 == nullptr) sweep_row<true, true, false>(row, m, j, mp, mp2, alpha, acc);
+    else sweep_row<true, true, true>(row, m, j, mp, mp2, alpha, acc);
     const float mn = block_reduce(acc.mn, INFINITY, OpMin(), fred);
     if (threadIdx.x == 0) m_new[j] = mn;
     if (do_eps) {
@@ -81,8 +111,7 @@ future_cost_finalize_kernel(const float *__restrict__ D3, int64_t ld, int64_t ro
     unsigned long long z = 0;
     const bool vec = (((reinterpret_cast<uintptr_t>(row) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0);
     const int64_t mv = vec ? (m & ~int64_t(3)) : 0;
-    for (int64_t k = int64_t(threadIdx.x) * 4; k < mv; k += ST * 4) {
-        float4 v = ld_stream_f4(row + k);
+    auto one = [&](float4 v, int64_t k) {
         if (use_a) {
             const float4 a = *reinterpret_cast<const float4 *>(mvec + k);
             v.x = __fadd_rn(v.x, __fmul_rn(alpha, a.x));
@@ -93,7 +122,14 @@ future_cost_finalize_kernel(const float *__restrict__ D3, int64_t ld, int64_t ro
         *reinterpret_cast<float4 *>(dst + k) = v;
         s += (double)v.x + (double)v.y + (double)v.z + (double)v.w;
         z += (v.x != 0.f) + (v.y != 0.f) + (v.z != 0.f) + (v.w != 0.f);
+    };
+    int64_t k = int64_t(threadIdx.x) * 4;
+    for (; k + 3 * ST * 4 < mv; k += 4 * ST * 4) {
+        const float4 v0 = ld_stream_f4(row + k), v1 = ld_stream_f4(row + k + ST * 4),
+                     v2 = ld_stream_f4(row + k + 2 * ST * 4), v3 = ld_stream_f4(row + k + 3 * ST * 4);
+        one(v0, k); one(v1, k + ST * 4); one(v2, k + 2 * ST * 4); one(v3, k + 3 * ST * 4);
     }
+    for (; k < mv; k += ST * 4) one(ld_stream_f4(row + k), k);
     for (int64_t k = mv + threadIdx.x; k < m; k += ST) {
         float v = row[k];
         if (use_a) v = __fadd_rn(v, __fmul_rn(alpha, mvec[k]));

@@ -17,9 +17,10 @@
 //               the epilogue.
 //   warps 2-5   epilogue: tcgen05.ld 32 lanes x 32 columns at a time, fused  n_r + n_c - 2g -> sqrt,
 //               direct + mirrored stores, fused fp64 sum / non-zero count for sigma.
-//   Tiles are visited in groups of 8 row-tiles so one wave's operand footprint stays inside L2;
+//   Tiles are visited in groups of 16 row-tiles (8 for the 2-CTA kernel) so one wave's operand footprint stays inside L2;
 //   in symmetric mode only tiles touching the upper triangle are computed (~half the MMAs).
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -33,10 +34,12 @@ constexpr int STAGES = 4;
 constexpr int A_BYTES = BM * BKB;       // 16 KB
 constexpr int B_BYTES = BN * BKB;       // 32 KB
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-constexpr int GROUP_M = 8;
+constexpr int GROUP_M = 16;
 constexpr int NUM_THREADS = 192;
 constexpr int TMEM_COLS = 512;
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int EPI_PITCH = 33;                              // epilogue transpose tile pitch (floats)
+constexpr int EPI_SMEM_BYTES = 4 * 32 * EPI_PITCH * 4;     // one 32 x 33 tile per epilogue warp
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + EPI_SMEM_BYTES;
 
 // kind::i8 instruction descriptor (cute/arch/mma_sm100_desc.hpp bit layout):
 //   c_format[4,6)=2 (S32) | a_format[7,10)=1 (s8) | b_format[10,13)=1 (s8) | a/b major = K (0)
@@ -136,9 +139,101 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// ------------------------------------------------------------------ epilogue (shared by both kernels)
+struct EpiStats {
+    double s;
+    unsigned long long z;
+};
+
+// One warp drains its 32 TMEM lanes (rows r0 .. r0+31 of the output) x BN accumulator columns:
+// d^2 = n_r + n_c - 2g (exact, mod 2^32), fp32 sqrt.  Each lane owns one output ROW, so a direct
+// store would write 4-16 B per row per instruction: partial 32 B sectors that L2 has to fill from
+// DRAM (measured: 3.3 GB of extra DRAM reads for a 1.6 GB D1).  The 32 x 32 chunk is therefore
+// transposed through a per-warp shared-memory tile (33-float pitch, conflict-free both ways) and
+// every global store instruction writes one full 128 B line; the mirrored store D[c][r] is
+// coalesced as it is (lanes <-> consecutive r).  Symmetric mode handles r <= c only.
+// `release()` is called by lane 0 once the warp's last TMEM read has completed, so the MMA warp can
+// reuse the accumulator while the stores drain.
+
+template <typename Release>
+__device__ __forceinline__ void epilogue_tile(const GramArgs &args, uint32_t t_base, int64_t r0, int64_t c0,
+                                              int lane, float *tile, Release release, EpiStats &st) {
+    const int64_t row_end = args.row0 + args.rows;
+    const int64_t r = r0 + lane;
+    const bool r_ok = r < row_end;
+    const uint32_t nr = r_ok ? (uint32_t)__ldg(args.sqnorm + r) : 0u;
+    int64_t rows_here = row_end - r0;                              // valid rows of this warp's 32
+    if (rows_here > 32) rows_here = 32;
+#pragma unroll 1
+    for (int cc = 0; cc < BN / 32; ++cc) {
+        uint32_t g[32];
+        tmem_ld32(t_base + cc * 32, g);
+        if (cc == BN / 32 - 1) {                                  // all of this warp's reads are done
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) release();
+        }
+        const int64_t cbase = c0 + cc * 32;
+        if (cbase >= args.n || rows_here <= 0) continue;
+        if (args.symmetric && cbase + 31 < r0) continue;          // whole chunk below the diagonal for this warp
+        const uint32_t nc_lane = (cbase + lane < args.n) ? (uint32_t)__ldg(args.sqnorm + cbase + lane) : 0u;
+        __syncwarp();                                             // previous chunk's tile reads are finished
+        // sigma statistics: fp32 / int partials per 32-element chunk, promoted to fp64 once per chunk
+        // (a per-element DFMA chain made the epilogue, not the MMAs, the critical path at K = 12288)
+        float cs = 0.f;
+        int cz = 0;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            const uint32_t nc = __shfl_sync(0xffffffffu, nc_lane, j);
+            const uint32_t d2 = nr + nc - 2u * g[j];              // exact mod 2^32
+            const float d = __fsqrt_rn(__uint2float_rn(d2));
+            tile[lane * EPI_PITCH + j] = d;
+            const int64_t c = cbase + j;
+            if (args.symmetric && r_ok && c < args.n && r < c) {
+                args.D[c * args.ldd + r] = d;                     // mirrored store: coalesced across the warp
+                cs += d;
+                cz += (d != 0.f);
+            }
+        }
+        __syncwarp();
+        const int64_t c = cbase + lane;                           // this lane's column for the row stores
+        const bool c_ok = c < args.n;
+        float *dst = args.D + (r0 - args.row0) * args.ldd + c;
+        if (!args.symmetric) {
+#pragma unroll 8
+            for (int i = 0; i < 32; ++i) {
+                if (i < rows_here && c_ok) {
+                    const float d = tile[i * EPI_PITCH + lane];
+                    dst[i * args.ldd] = d;
+                    cs += d;
+                    cz += (d != 0.f);
+                }
+            }
+            st.s += (double)cs;
+            st.z += (unsigned long long)cz;
+        } else {
+#pragma unroll 8
+            for (int i = 0; i < 32; ++i)
+                if (i < rows_here && c_ok && r0 + i <= c) dst[i * args.ldd] = tile[i * EPI_PITCH + lane];
+            st.s += 2.0 * (double)cs;                             // each off-diagonal distance appears twice
+            st.z += 2ull * (unsigned long long)cz;
+        }
+    }
+}
+
+__device__ __forceinline__ void epilogue_flush(const GramArgs &args, EpiStats &st, int lane) {
+    if (args.sum != nullptr) {
+        const double s = warp_sum(st.s);
+        const unsigned long long z = warp_sum(st.z);
+        if (lane == 0) { atomicAdd(args.sum, s); atomicAdd(args.nnz, z); }
+    }
+}
+
 // ------------------------------------------------------------------ tile schedule
 // Row-tiles are taken in groups of GROUP_M; inside a group the order is column-major, so a wave of
-// CTAs shares <= GROUP_M A-tiles and ~148/GROUP_M B-tiles (L2 footprint instead of DRAM streaming).
+// CTAs shares <= GROUP_M A-tiles and ~148/GROUP_M B-tiles: a roughly square super-tile minimises the
+// rows a wave must pull through L2 (measured at N=20000, K=12288: DRAM reads 12x the operand size
+// with groups of 4 x 256 rows).
 // Symmetric mode keeps tile (tm, tn) iff it intersects the upper triangle: tn >= tm / 2.
 __host__ __device__ inline int sym_group_count(int g, int TM, int TN, int *gm_out) {
     const int first = g * GROUP_M;
@@ -266,84 +361,239 @@ gram_l2_s8_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     } else {
         // ===================== epilogue (warps 2..5) =====================
         const int quarter = warp & 3;                                     // TMEM lane quarter this warp may read
-        const int row_in_tile = quarter * 32 + lane;
+        float *epi_tile = reinterpret_cast<float *>(smem_raw + (bars + 256 - raw)) + (warp - 2) * 32 * EPI_PITCH;
         int acc = 0;
         uint32_t acc_phase = 0;
-        double s_acc = 0.0;
-        unsigned long long z_acc = 0;
-        const int64_t row_end = args.row0 + args.rows;
+        EpiStats st{0.0, 0ull};
         for (int t = blockIdx.x; t < args.num_tiles; t += gridDim.x) {
             int tm, tn;
             decode_tile(t, args.TM, args.TN, args.symmetric, &tm, &tn);
-            const int64_t r = args.row0 + int64_t(tm) * BM + row_in_tile;
-            const int64_t c0 = int64_t(tn) * BN;
-            const bool r_ok = r < row_end;
-            const uint32_t nr = r_ok ? (uint32_t)__ldg(args.sqnorm + r) : 0u;
-            float *drow = args.D + (r - args.row0) * args.ldd;
-            const bool vec_ok = ((reinterpret_cast<uintptr_t>(drow) & 15) == 0);
             mbar_wait(tfull_bar + 8 * acc, acc_phase);
             tc_fence_after();
             const uint32_t t_base = tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(acc * BN);
-#pragma unroll 1
-            for (int cc = 0; cc < BN / 32; ++cc) {
-                uint32_t g[32];
-                tmem_ld32(t_base + cc * 32, g);
-                if (cc == BN / 32 - 1) {                                  // all of this warp's reads are done
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(tempty_bar + 8 * acc);
-                }
-                const int64_t cbase = c0 + cc * 32;
-                if (cbase >= args.n) continue;
-                if (args.symmetric && cbase + 31 < args.row0 + int64_t(tm) * BM + quarter * 32) continue;  // whole chunk below diagonal for this warp
-                float d[32];
-#pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const int64_t c = cbase + j;
-                    const uint32_t nc = (c < args.n) ? (uint32_t)__ldg(args.sqnorm + c) : 0u;
-                    const uint32_t d2 = nr + nc - 2u * g[j];              // exact mod 2^32
-                    d[j] = __fsqrt_rn(__uint2float_rn(d2));
-                }
-                if (!args.symmetric) {
-                    if (r_ok) {
-                        if (vec_ok && cbase + 32 <= args.n) {
-#pragma unroll
-                            for (int j = 0; j < 32; j += 4)
-                                *reinterpret_cast<float4 *>(drow + cbase + j) = make_float4(d[j], d[j + 1], d[j + 2], d[j + 3]);
-#pragma unroll
-                            for (int j = 0; j < 32; ++j) { s_acc += (double)d[j]; z_acc += (d[j] != 0.f); }
-                        } else {
-#pragma unroll
-                            for (int j = 0; j < 32; ++j)
-                                if (cbase + j < args.n) { drow[cbase + j] = d[j]; s_acc += (double)d[j]; z_acc += (d[j] != 0.f); }
-                        }
-                    }
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const int64_t c = cbase + j;
-                        if (r_ok && c < args.n && r <= c) {
-                            drow[c] = d[j];
-                            if (r < c) {
-                                args.D[c * args.ldd + r] = d[j];          // mirrored store: coalesced across the warp
-                                s_acc += 2.0 * (double)d[j];
-                                z_acc += 2ull * (d[j] != 0.f);
-                            }
-                        }
-                    }
-                }
-            }
+            const uint32_t release = tempty_bar + 8 * acc;
+            epilogue_tile(args, t_base, args.row0 + int64_t(tm) * BM + quarter * 32, int64_t(tn) * BN, lane,
+                          epi_tile, [release]() { mbar_arrive(release); }, st);
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
-        if (args.sum != nullptr) {
-            s_acc = warp_sum(s_acc);
-            z_acc = warp_sum(z_acc);
-            if (lane == 0) { atomicAdd(args.sum, s_acc); atomicAdd(args.nnz, z_acc); }
-        }
+        epilogue_flush(args, st, lane);
     }
     tc_fence_before();
     __syncthreads();
     if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+// ------------------------------------------------------------------ 2-CTA (cta_group::2) variant
+// A CTA pair (cluster of 2, same TPC) computes one 256 x 256 tile: each CTA holds 128 rows of A and
+// 128 of the 256 B rows in its own shared memory, the leader issues tcgen05.mma.cta_group::2 (M = 256)
+// and each CTA's TMEM receives its own 128 output rows.  Per CTA and per 128-byte K block this halves
+// the operand bytes TMA must write and the tensor core must read from shared memory (32 KB instead
+// of 48 KB for the same 512 MMA cycles): the 1-CTA kernel is shared-memory-bandwidth bound
+// (16 KB A + 32 KB B read + 48 KB TMA fill per 512 MMA cycles > 128 B/cycle).
+constexpr int BM2 = 256;                              // rows per cluster tile
+constexpr int STAGES2 = 6;
+constexpr int STAGE2_BYTES = 2 * A_BYTES;             // A half (128 rows) + B half (128 rows)
+constexpr int GROUP_M2 = 8;
+constexpr int SMEM2_BYTES = STAGES2 * STAGE2_BYTES + 1024 + 256 + EPI_SMEM_BYTES;
+constexpr uint32_t IDESC_S8_2CTA = (2u << 4) | (1u << 7) | (1u << 10) | (uint32_t(BN >> 3) << 17) |
+                                   (uint32_t(BM2 >> 4) << 24);
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the barrier at the same shared-memory offset in CTA `cta` of the cluster
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar, uint32_t cta) {
+    asm volatile(
+        "{\n\t.reg .b32 remote;\n\t"
+        "mapa.shared::cluster.u32 remote, %0, %1;\n\t"
+        "mbarrier.arrive.shared::cluster.b64 _, [remote];\n\t}"
+        ::"r"(bar), "r"(cta) : "memory");
+}
+// 2-SM TMA load: data lands in THIS CTA's shared memory, completion bytes are credited to the
+// leader CTA's mbarrier (peer bit of the shared::cluster address cleared).
+__device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar & 0xFEFFFFFFu), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_2cta(uint32_t dst_smem, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+}
+__device__ __forceinline__ void tmem_dealloc_2cta(uint32_t taddr, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols));
+}
+__device__ __forceinline__ void umma_commit_2cta(uint32_t bar) {          // arrives in both CTAs of the pair
+    asm volatile(
+        "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+        ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void umma_s8_2cta(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                             uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+
+// 256 x 256 tiles; symmetric mode keeps (tm, tn) iff tn >= tm.  Groups of GROUP_M2 row-tiles,
+// column-major inside a group (same L2 argument as the 1-CTA schedule).
+__host__ __device__ inline int sym2_group_count(int g, int TM, int TN, int *gm_out) {
+    const int first = g * GROUP_M2;
+    const int gm = (TM - first < GROUP_M2) ? (TM - first) : GROUP_M2;
+    int cnt = 0;
+    for (int j = 0; j < GROUP_M2; ++j)
+        if (first + j < TN) cnt += (gm < j + 1) ? gm : (j + 1);
+    const int full = TN - (first + GROUP_M2);
+    if (full > 0) cnt += full * gm;
+    *gm_out = gm;
+    return cnt;
+}
+
+__host__ __device__ inline void decode_tile2(int t, int TM, int TN, int symmetric, int *tm, int *tn) {
+    if (!symmetric) {
+        const int per_group = GROUP_M2 * TN;
+        const int g = t / per_group;
+        const int first = g * GROUP_M2;
+        const int gm = (TM - first < GROUP_M2) ? (TM - first) : GROUP_M2;
+        const int rem = t - g * per_group;
+        *tn = rem / gm;
+        *tm = first + rem % gm;
+        return;
+    }
+    for (int g = 0;; ++g) {
+        int gm;
+        const int cnt = sym2_group_count(g, TM, TN, &gm);
+        if (t < cnt) {
+            const int first = g * GROUP_M2;
+            for (int j = 0; j < GROUP_M2; ++j) {
+                if (first + j >= TN) break;
+                const int c = (gm < j + 1) ? gm : (j + 1);
+                if (t < c) { *tm = first + t; *tn = first + j; return; }
+                t -= c;
+            }
+            *tm = first + t % gm;
+            *tn = first + GROUP_M2 + t / gm;
+            return;
+        }
+        t -= cnt;
+    }
+}
+
+int count_tiles2(int TM, int TN, int symmetric) {
+    if (!symmetric) return TM * TN;
+    int total = 0, gm;
+    for (int g = 0; g * GROUP_M2 < TM; ++g) total += sym2_group_count(g, TM, TN, &gm);
+    return total;
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
+gram_l2_s8_2cta_kernel(const __grid_constant__ CUtensorMap map, const GramArgs args) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t tiles = (raw + 1023u) & ~1023u;
+    const uint32_t bars = tiles + STAGES2 * STAGE2_BYTES;
+    const uint32_t full_bar = bars, empty_bar = bars + 8 * STAGES2;
+    const uint32_t tfull_bar = bars + 16 * STAGES2, tempty_bar = tfull_bar + 16;
+    const uint32_t tmem_slot = tempty_bar + 16;
+    uint32_t *tmem_slot_ptr = reinterpret_cast<uint32_t *>(smem_raw + (tmem_slot - raw));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = (rank == 0);
+    const int KB = int(args.kp / BKB);
+    const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map) : "memory");
+        for (int s = 0; s < STAGES2; ++s) { mbar_init(full_bar + 8 * s, 2); mbar_init(empty_bar + 8 * s, 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar + 8 * s, 1); mbar_init(tempty_bar + 8 * s, 8); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) tmem_alloc_2cta(tmem_slot, TMEM_COLS);
+    tc_fence_before();
+    cluster_sync_all();                                   // peer barriers initialised, both TMEM allocations done
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+
+    if (warp == 0) {
+        // ===================== TMA producer (both CTAs) =====================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int t = cluster_id; t < args.num_tiles; t += num_clusters) {
+                int tm, tn;
+                decode_tile2(t, args.TM, args.TN, args.symmetric, &tm, &tn);
+                int row_a = int(args.row0) + tm * BM2 + int(rank) * BM;
+                int row_b = tn * BN + int(rank) * (BN / 2);
+                if (row_a >= args.n) row_a = 0;           // fully out-of-range half: load anything, stores are masked
+                if (row_b >= args.n) row_b = 0;
+                for (int kb = 0; kb < KB; ++kb) {
+                    mbar_wait(empty_bar + 8 * stage, phase ^ 1);
+                    const uint32_t sa = tiles + stage * STAGE2_BYTES, sb = sa + A_BYTES;
+                    if (leader) mbar_arrive_expect_tx(full_bar + 8 * stage, 2 * STAGE2_BYTES);
+                    else mbar_arrive_cluster(full_bar + 8 * stage, 0);
+                    tma_load_2d_2sm(sa, &map, full_bar + 8 * stage, kb * BKB, row_a);
+                    tma_load_2d_2sm(sb, &map, full_bar + 8 * stage, kb * BKB, row_b);
+                    if (++stage == STAGES2) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer (leader CTA only) =====================
+        if (leader && lane == 0) {
+            int stage = 0, acc = 0;
+            uint32_t phase = 0, acc_phase = 0;
+            for (int t = cluster_id; t < args.num_tiles; t += num_clusters) {
+                mbar_wait(tempty_bar + 8 * acc, acc_phase ^ 1);          // both CTAs' epilogues drained this buffer
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + uint32_t(acc * BN);
+                for (int kb = 0; kb < KB; ++kb) {
+                    mbar_wait(full_bar + 8 * stage, phase);               // both CTAs' TMA bytes have landed
+                    tc_fence_after();
+                    const uint32_t sa = tiles + stage * STAGE2_BYTES, sb = sa + A_BYTES;
+                    const uint64_t da = make_desc_sw128(sa), db = make_desc_sw128(sb);
+#pragma unroll
+                    for (int k = 0; k < BKB / UMMA_KB; ++k)
+                        umma_s8_2cta(d_tmem, da + uint64_t(k * (UMMA_KB >> 4)), db + uint64_t(k * (UMMA_KB >> 4)),
+                                     IDESC_S8_2CTA, (kb | k) != 0);
+                    umma_commit_2cta(empty_bar + 8 * stage);              // frees the stage in both CTAs
+                    if (++stage == STAGES2) { stage = 0; phase ^= 1; }
+                }
+                umma_commit_2cta(tfull_bar + 8 * acc);                    // accumulators complete in both CTAs
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else {
+        // ===================== epilogue (warps 2..5, both CTAs: own 128 rows) =====================
+        const int quarter = warp & 3;
+        float *epi_tile = reinterpret_cast<float *>(smem_raw + (bars + 256 - raw)) + (warp - 2) * 32 * EPI_PITCH;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        EpiStats st{0.0, 0ull};
+        for (int t = cluster_id; t < args.num_tiles; t += num_clusters) {
+            int tm, tn;
+            decode_tile2(t, args.TM, args.TN, args.symmetric, &tm, &tn);
+            mbar_wait(tfull_bar + 8 * acc, acc_phase);
+            tc_fence_after();
+            const uint32_t t_base = tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(acc * BN);
+            const uint32_t release = tempty_bar + 8 * acc;
+            epilogue_tile(args, t_base, args.row0 + int64_t(tm) * BM2 + int64_t(rank) * BM + quarter * 32,
+                          int64_t(tn) * BN, lane, epi_tile, [release]() { mbar_arrive_cluster(release, 0); }, st);
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+        epilogue_flush(args, st, lane);
+    }
+    tc_fence_before();
+    cluster_sync_all();
+    if (warp == 1) tmem_dealloc_2cta(tmem_base, TMEM_COLS);
 }
 
 // ------------------------------------------------------------------ host side
@@ -405,6 +655,23 @@ extern "C" int avtex_gram_l2_s8(const int8_t *packed, int64_t n, int64_t kp, con
     a.n = n; a.kp = kp; a.row0 = row0; a.rows = rows; a.ldd = ldd;
     a.sqnorm = sqnorm; a.D = D; a.sum = sum; a.nnz = nnz;
     a.symmetric = symmetric ? 1 : 0;
+    const char *mode = getenv("AVTEX_GRAM_MODE");                  // "1cta" selects the single-CTA kernel
+    const bool two_cta = !(mode != nullptr && mode[0] == '1');
+    if (two_cta) {
+        a.TM = int((rows + BM2 - 1) / BM2);
+        a.TN = int((n + BN - 1) / BN);
+        a.num_tiles = count_tiles2(a.TM, a.TN, a.symmetric);
+        static bool attr2_set[64] = {false};
+        if (device < 64 && !attr2_set[device]) {
+            AVTEX_CUDA(cudaFuncSetAttribute(gram_l2_s8_2cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES));
+            attr2_set[device] = true;
+        }
+        int clusters = sms / 2;
+        if (a.num_tiles < clusters) clusters = a.num_tiles;
+        gram_l2_s8_2cta_kernel<<<2 * clusters, NUM_THREADS, SMEM2_BYTES, as_stream(stream)>>>(map_a, a);
+        AVTEX_LAUNCH_CHECK();
+        return 0;
+    }
     a.TM = int((rows + BM - 1) / BM);
     a.TN = int((n + BN - 1) / BN);
     a.num_tiles = count_tiles(a.TM, a.TN, a.symmetric);
@@ -417,6 +684,13 @@ extern "C" int avtex_gram_l2_s8(const int8_t *packed, int64_t n, int64_t kp, con
     gram_l2_s8_kernel<<<grid, NUM_THREADS, SMEM_BYTES, as_stream(stream)>>>(map_a, map_b, a);
     AVTEX_LAUNCH_CHECK();
     return 0;
+}
+
+extern "C" int avtex_gram_tile_schedule2(int TM, int TN, int symmetric, int *tm_out, int *tn_out, int capacity) {
+    const int total = count_tiles2(TM, TN, symmetric);
+    if (tm_out == nullptr) return total;
+    for (int t = 0; t < total && t < capacity; ++t) decode_tile2(t, TM, TN, symmetric, &tm_out[t], &tn_out[t]);
+    return total;
 }
 
 // Exposed for tests: the tile schedule must cover every needed tile exactly once.

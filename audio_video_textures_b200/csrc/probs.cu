@@ -41,10 +41,17 @@ sum_nnz_kernel(const float *__restrict__ D, int64_t rows, int64_t cols, int64_t 
 // exp((-d)/sigma): true division, as `torch.exp(-D / sigma)`.
 __device__ __forceinline__ float trans_e(float d, float sigma) { return expf(__fdiv_rn(-d, sigma)); }
 
-__global__ void __launch_bounds__(PT)
+// CACHE: E = exp(-D/sigma) of the whole row is kept in shared memory between the two passes, so the
+// row is read from HBM once and exp is evaluated once (rows up to PROBS_SMEM_COLS floats); otherwise
+// pass 2 re-reads the row and recomputes exp (deterministic -> identical values).
+constexpr int PROBS_SMEM_COLS = 48 * 1024;
+
+template <bool CACHE, int NT>
+__global__ void __launch_bounds__(NT)
 transition_probs_kernel(const float *__restrict__ D, int64_t ld, int64_t rows_in, int64_t cols,
                         float sigma, int shift, float *__restrict__ P, int64_t ldp, float th,
                         float *__restrict__ Pn, int64_t ldn, int *__restrict__ counts) {
+    extern __shared__ float ebuf[];
     __shared__ double dred[32];
     __shared__ float fred[32];
     __shared__ int ired[32];
@@ -57,34 +64,61 @@ transition_probs_kernel(const float *__restrict__ D, int64_t ld, int64_t rows_in
     // pass 1: row sum (fp64) and row max of E
     double s = 0.0;
     float mx = 0.f;                                   // E > 0 always
-    for (int64_t k = int64_t(threadIdx.x) * 4; k < cv; k += PT * 4) {
-        const float4 v = *reinterpret_cast<const float4 *>(src + k);
+    auto one4 = [&](const float4 v, int64_t k) {
         const float e0 = trans_e(v.x, sigma), e1 = trans_e(v.y, sigma), e2 = trans_e(v.z, sigma),
                     e3 = trans_e(v.w, sigma);
+        if (CACHE) *reinterpret_cast<float4 *>(ebuf + k) = make_float4(e0, e1, e2, e3);
         s += (double)e0 + (double)e1 + (double)e2 + (double)e3;
         mx = fmaxf(fmaxf(mx, fmaxf(e0, e1)), fmaxf(e2, e3));
+    };
+    int64_t k = int64_t(threadIdx.x) * 4;
+    for (; k + NT * 4 < cv; k += 2 * NT * 4) {        // two 128-bit loads in flight
+        const float4 v0 = CACHE ? ld_stream_f4(src + k) : *reinterpret_cast<const float4 *>(src + k);
+        const float4 v1 = CACHE ? ld_stream_f4(src + k + NT * 4) : *reinterpret_cast<const float4 *>(src + k + NT * 4);
+        one4(v0, k);
+        one4(v1, k + NT * 4);
     }
-    for (int64_t k = cv + threadIdx.x; k < cols; k += PT) {
-        const float e = trans_e(src[k], sigma);
+    for (; k < cv; k += NT * 4) one4(CACHE ? ld_stream_f4(src + k) : *reinterpret_cast<const float4 *>(src + k), k);
+    for (int64_t t = cv + threadIdx.x; t < cols; t += NT) {
+        const float e = trans_e(src[t], sigma);
+        if (CACHE) ebuf[t] = e;
         s += (double)e;
         mx = fmaxf(mx, e);
     }
-    s = block_reduce(s, 0.0, OpAdd<double>(), dred);
+    s = block_reduce(s, 0.0, OpAdd<double>(), dred);             // (also orders the ebuf writes)
     mx = block_reduce(mx, 0.f, OpMax(), fred);
     const float S = (float)s;
     const float pmax = __fdiv_rn(mx, S);                         // division is monotone: max P = fl(max E / S)
     const float cut = __fsub_rn(pmax, __fmul_rn(th, pmax));      // q_learning.py:63
-    // pass 2: the row is re-read from L1/L2, exp recomputed (deterministic -> identical values)
     float *dp = (P != nullptr) ? P + i * ldp : nullptr;
     float *dn = (Pn != nullptr) ? Pn + i * ldn : nullptr;
     int cnt = 0;
-    for (int64_t k = threadIdx.x; k < cols; k += PT) {
-        const float pv = __fdiv_rn(trans_e(src[k], sigma), S);
-        if (dp != nullptr) dp[k] = pv;
+    const bool vec_out = vec && (dp == nullptr || (reinterpret_cast<uintptr_t>(dp) & 15) == 0) &&
+                         (dn == nullptr || (reinterpret_cast<uintptr_t>(dn) & 15) == 0);
+    const int64_t cw = vec_out ? cv : 0;
+    for (int64_t q = int64_t(threadIdx.x) * 4; q < cw; q += NT * 4) {
+        float4 e;
+        if (CACHE) e = *reinterpret_cast<const float4 *>(ebuf + q);
+        else {
+            const float4 v = *reinterpret_cast<const float4 *>(src + q);
+            e = make_float4(trans_e(v.x, sigma), trans_e(v.y, sigma), trans_e(v.z, sigma), trans_e(v.w, sigma));
+        }
+        float4 pv = make_float4(__fdiv_rn(e.x, S), __fdiv_rn(e.y, S), __fdiv_rn(e.z, S), __fdiv_rn(e.w, S));
+        if (dp != nullptr) *reinterpret_cast<float4 *>(dp + q) = pv;
+        if (dn != nullptr) {
+            pv.x = (pv.x < cut) ? 0.f : pv.x; pv.y = (pv.y < cut) ? 0.f : pv.y;
+            pv.z = (pv.z < cut) ? 0.f : pv.z; pv.w = (pv.w < cut) ? 0.f : pv.w;
+            *reinterpret_cast<float4 *>(dn + q) = pv;
+        }
+        cnt += (pv.x != 0.f) + (pv.y != 0.f) + (pv.z != 0.f) + (pv.w != 0.f);
+    }
+    for (int64_t q = cw + threadIdx.x; q < cols; q += NT) {
+        const float pv = __fdiv_rn(CACHE ? ebuf[q] : trans_e(src[q], sigma), S);
+        if (dp != nullptr) dp[q] = pv;
         float out = pv;
         if (dn != nullptr) {
             out = (pv < cut) ? 0.f : pv;
-            dn[k] = out;
+            dn[q] = out;
         }
         cnt += (out != 0.f);
     }
@@ -158,8 +192,26 @@ extern "C" int avtex_transition_probs(const float *D, int64_t ld, int64_t rows_i
     AVTEX_REQUIRE(P == nullptr || ldp >= cols, "transition_probs: ldp too small");
     AVTEX_REQUIRE(P_new == nullptr || (ldn >= cols && th >= 0.f), "transition_probs: P_new needs ldn >= cols and th >= 0");
     AVTEX_REQUIRE(sigma > 0.f, "transition_probs: sigma must be positive (got %g)", (double)sigma);
-    transition_probs_kernel<<<(unsigned)rows_out, PT, 0, as_stream(stream)>>>(
-        D, ld, rows_in, cols, sigma, shift, P, ldp, th, P_new, ldn, counts);
+    if (cols <= PROBS_SMEM_COLS) {
+        const size_t smem = (size_t)cols * sizeof(float);
+        static bool attr_set[64] = {false};
+        if (device >= 0 && device < 64 && !attr_set[device]) {
+            AVTEX_CUDA(cudaFuncSetAttribute(transition_probs_kernel<true, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            PROBS_SMEM_COLS * (int)sizeof(float)));
+            AVTEX_CUDA(cudaFuncSetAttribute(transition_probs_kernel<true, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            PROBS_SMEM_COLS * (int)sizeof(float)));
+            attr_set[device] = true;
+        }
+        if (cols >= 8192)       // long rows: few CTAs fit per SM (shared memory), so make each one wide
+            transition_probs_kernel<true, 1024><<<(unsigned)rows_out, 1024, smem, as_stream(stream)>>>(
+                D, ld, rows_in, cols, sigma, shift, P, ldp, th, P_new, ldn, counts);
+        else
+            transition_probs_kernel<true, 256><<<(unsigned)rows_out, 256, smem, as_stream(stream)>>>(
+                D, ld, rows_in, cols, sigma, shift, P, ldp, th, P_new, ldn, counts);
+    } else {
+        transition_probs_kernel<false, 1024><<<(unsigned)rows_out, 1024, 0, as_stream(stream)>>>(
+            D, ld, rows_in, cols, sigma, shift, P, ldp, th, P_new, ldn, counts);
+    }
     AVTEX_LAUNCH_CHECK();
     return 0;
 }

@@ -35,6 +35,15 @@ def _f32(x) -> np.float32:
     return np.float32(x)
 
 
+def empty_matrix(rows: int, cols: int, device, dtype=torch.float32) -> torch.Tensor:
+    """[rows, cols] view of a buffer whose leading dimension is padded to 128 bytes, so every row
+    starts 16-byte aligned and the kernels' 128-bit paths apply to all rows (an odd M such as 1241
+    or 19961 would otherwise leave 3 of 4 rows on the scalar path)."""
+    per = 128 // torch.empty(0, dtype=dtype).element_size()
+    ld = (cols + per - 1) // per * per
+    return torch.empty((rows, ld), dtype=dtype, device=device)[:, :cols]
+
+
 # --------------------------------------------------------------------------- stats / sigma
 def new_stats(device) -> torch.Tensor:
     """16-byte accumulator: [fp64 sum | uint64 nnz]."""
@@ -115,7 +124,7 @@ def gram_l2(pf: PackedFrames, row0: int = 0, rows: int | None = None, symmetric:
     rows = n - row0 if rows is None else rows
     if symmetric is None:
         symmetric = (row0 == 0 and rows == n)
-    D = torch.empty((rows, n), dtype=torch.float32, device=pf.packed.device) if out is None else out
+    D = empty_matrix(rows, n, pf.packed.device) if out is None else out
     s, z = _stats_ptrs(stats)
     _lib.call("avtex_gram_l2_s8", _lib.ptr(pf.packed), n, kp, _lib.ptr(pf.sqnorm), row0, rows,
               1 if symmetric else 0, _lib.ptr(D), D.stride(0), s, z, _dev(D), _stream(D))
@@ -130,7 +139,7 @@ def pairdist_direct(frames: torch.Tensor, row0: int = 0, rows: int | None = None
         x = x.contiguous()
     n, k = x.shape
     rows = n - row0 if rows is None else rows
-    D = torch.empty((rows, n), dtype=torch.float32, device=x.device)
+    D = empty_matrix(rows, n, x.device)
     s, z = _stats_ptrs(stats)
     name = {torch.float32: "avtex_pairdist_direct_f32", torch.uint8: "avtex_pairdist_direct_u8"}.get(x.dtype)
     if name is None:
@@ -159,12 +168,13 @@ def transition_probs(D: torch.Tensor, sigma, shift: int = 1, rows_out: int | Non
     """P (and thresholded P_new) for output rows [0, rows_out) from source rows min(i+shift, rows-1)."""
     rows_in, cols = D.shape
     rows_out = rows_in if rows_out is None else rows_out
-    P = torch.empty((rows_out, cols), dtype=torch.float32, device=D.device) if want_P else None
-    Pn = torch.empty((rows_out, cols), dtype=torch.float32, device=D.device) if threshold is not None else None
+    P = empty_matrix(rows_out, cols, D.device) if want_P else None
+    Pn = empty_matrix(rows_out, cols, D.device) if threshold is not None else None
     counts = torch.empty(rows_out, dtype=torch.int32, device=D.device) if want_counts else None
     th = _f32(threshold) if threshold is not None else np.float32(-1.0)
     _lib.call("avtex_transition_probs", _lib.ptr(D), D.stride(0), rows_in, cols, C.c_float(_f32(sigma)), shift,
-              rows_out, _lib.ptr(P), cols, C.c_float(th), _lib.ptr(Pn), cols, _lib.ptr(counts), _dev(D), _stream(D))
+              rows_out, _lib.ptr(P), P.stride(0) if P is not None else 0, C.c_float(th), _lib.ptr(Pn),
+              Pn.stride(0) if Pn is not None else 0, _lib.ptr(counts), _dev(D), _stream(D))
     return P, Pn, counts
 
 
@@ -204,12 +214,13 @@ def diag_filter(D1: torch.Tensor, filter_size: int, stride: int = 1, p: float | 
     taps = binomial_taps(filter_size) if taps is None else np.ascontiguousarray(taps, dtype=np.float32)
     if taps.shape[0] != filter_size:
         raise ValueError("taps length != filter_size")
-    D2 = torch.empty((rows_out, m), dtype=torch.float32, device=D1.device)
-    D3 = torch.empty((rows_out, m), dtype=torch.float32, device=D1.device) if p is not None else None
+    D2 = empty_matrix(rows_out, m, D1.device)
+    D3 = empty_matrix(rows_out, m, D1.device) if p is not None else None
     s, z = _stats_ptrs(stats)
     _lib.call("avtex_diag_filter_pow", _lib.ptr(D1), D1.stride(0), in_row0, D1.shape[0],
               taps.ctypes.data_as(C.POINTER(C.c_float)), filter_size, stride, a0, rows_out, m,
-              _lib.ptr(D2), m, _lib.ptr(D3), m, C.c_float(_f32(p if p is not None else 1.0)), s, z,
+              _lib.ptr(D2), D2.stride(0), _lib.ptr(D3), D3.stride(0) if D3 is not None else 0,
+              C.c_float(_f32(p if p is not None else 1.0)), s, z,
               _dev(D1), _stream(D1))
     return D2, D3
 
@@ -271,10 +282,10 @@ def future_cost_finalize(D3: torch.Tensor, mvec: torch.Tensor, alpha: float = 0.
                          m: int | None = None, stats: torch.Tensor | None = None) -> torch.Tensor:
     rows = D3.shape[0]
     m = D3.shape[1] if m is None else m
-    out = torch.empty((rows, m), dtype=torch.float32, device=D3.device)
+    out = empty_matrix(rows, m, D3.device)
     s, z = _stats_ptrs(stats)
     _lib.call("avtex_future_cost_finalize", _lib.ptr(D3), D3.stride(0), row0, rows, m, _lib.ptr(mvec),
-              C.c_float(_f32(alpha)), _lib.ptr(out), m, s, z, _dev(D3), _stream(D3))
+              C.c_float(_f32(alpha)), _lib.ptr(out), out.stride(0), s, z, _dev(D3), _stream(D3))
     return out
 
 
@@ -312,11 +323,12 @@ def audio_start(x: torch.Tensor, d: torch.Tensor) -> int:
     return int(out.item())
 
 
-def gram_tile_schedule(TM: int, TN: int, symmetric: bool):
-    """Test hook (host only, no GPU): visiting order of the Gram tiles."""
+def gram_tile_schedule(TM: int, TN: int, symmetric: bool, two_cta: bool = False):
+    """Test hook (host only, no GPU): visiting order of the Gram tiles (128x256, or 256x256 for 2-CTA)."""
     lib = _lib.load()
-    total = lib.avtex_gram_tile_schedule(TM, TN, 1 if symmetric else 0, None, None, 0)
+    fn = lib.avtex_gram_tile_schedule2 if two_cta else lib.avtex_gram_tile_schedule
+    total = fn(TM, TN, 1 if symmetric else 0, None, None, 0)
     tm = (C.c_int * total)()
     tn = (C.c_int * total)()
-    lib.avtex_gram_tile_schedule(TM, TN, 1 if symmetric else 0, tm, tn, total)
+    fn(TM, TN, 1 if symmetric else 0, tm, tn, total)
     return list(zip(tm, tn))

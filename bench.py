@@ -39,6 +39,9 @@ WORKLOADS = {
     "c1": dict(n=300, h=64, w=64, m=1, fs=40, stride=1),
     "c2": dict(n=5000, h=224, w=224, m=3, fs=40, stride=4),
     "c5": dict(n=100000, h=64, w=64, m=3, fs=40, stride=4),
+    # not a BASELINE config: M = 19961 makes every M x M matrix 1.6 GB, far beyond L2 — used to
+    # measure the HBM-bound kernels (filter, sweep, finalize, probabilities) against the HBM roofline
+    "hbm": dict(n=20000, h=64, w=64, m=1, fs=40, stride=1),
 }
 METRIC = "frame-pairs/s (distance + temporal filter + converged future-cost)"
 L2_FLUSH_BYTES = 256 << 20

@@ -168,6 +168,8 @@ AVTEX_API int avtex_audio_start(const float *x, int64_t ld, int64_t rows, int64_
 /* Test hook: the tile visiting order of avtex_gram_l2_s8 for TM x TN tiles (128 x 256).  Returns the
  * number of tiles; fills tm_out/tn_out (capacity entries) when non-NULL.  Host only. */
 AVTEX_API int avtex_gram_tile_schedule(int TM, int TN, int symmetric, int *tm_out, int *tn_out, int capacity);
+/* Same for the default 2-CTA kernel (256 x 256 tiles; symmetric keeps tn >= tm). */
+AVTEX_API int avtex_gram_tile_schedule2(int TM, int TN, int symmetric, int *tm_out, int *tn_out, int capacity);
 
 #ifdef __cplusplus
 }

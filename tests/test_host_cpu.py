@@ -62,7 +62,7 @@ def test_gram_tile_schedule_rowblock_covers_all_once(TM, TN):
     s = engine.gram_tile_schedule(TM, TN, False)
     assert sorted(s) == [(a, b) for a in range(TM) for b in range(TN)]
     # groups of 8 row tiles, column-major inside a group (L2 footprint of a wave)
-    assert s[:min(8, TM)] == [(i, 0) for i in range(min(8, TM))]
+    assert s[:min(16, TM)] == [(i, 0) for i in range(min(16, TM))]
 
 
 def test_binomial_taps_and_sigma_arithmetic():
@@ -108,6 +108,15 @@ def test_argument_surfaces_match_reference_defaults():
             c.new_video_length, c.evaluate, c.da_feats) == (1, 0.1, 0.0, 0.5, 150, 20, 4, 30, False, "VGG")
     c = cvt_parser().parse_args("-e -th 0.3 -temp 0.1 -alpha 0.5 -mbs 100 -m 2".split())
     assert (c.evaluate, c.threshold, c.temp, c.alpha, c.mini_batchsize, c.model_type) == (True, 0.3, 0.1, 0.5, 100, 2)
+
+
+@pytest.mark.parametrize("T", [1, 2, 3, 4, 5, 9, 20, 391])
+def test_gram_tile_schedule_2cta(T):
+    from audio_video_textures_b200 import engine
+    s = engine.gram_tile_schedule(T, T, True, two_cta=True)
+    assert len(s) == len(set(s)) and set(s) == {(a, b) for a in range(T) for b in range(T) if b >= a}
+    s = engine.gram_tile_schedule(max(1, T // 3), T, False, two_cta=True)
+    assert sorted(s) == [(a, b) for a in range(max(1, T // 3)) for b in range(T)]
 
 
 @pytest.mark.parametrize("n,fs,stride,world", [(5000, 40, 4, 8), (300, 40, 1, 2), (100000, 40, 4, 8), (520, 40, 4, 3)])
