@@ -22,15 +22,18 @@ SIGNATURES = {
     "avtex_abi_version": [],
     "avtex_device_info": [_int, C.POINTER(_int), C.POINTER(_int)],
     "avtex_zero": [_p, _i64, _int, _p],
-    "avtex_pack_frames_u8": [_p, _i64, _i64, _i64, _p, _i64, _p, _int, _p],
-    "avtex_pack_frames_f32": [_p, _i64, _i64, _i64, _p, _i64, _p, _p, _int, _p],
+    "avtex_pack_frames_u8": [_p, _i64, _i64, _i64, _p, _i64, _p, _p, _int, _p],
+    "avtex_pack_frames_f32": [_p, _i64, _i64, _i64, _p, _i64, _p, _p, _p, _int, _p],
     "avtex_gram_l2_s8": [_p, _i64, _i64, _p, _i64, _i64, _int, _p, _i64, _p, _p, _int, _p],
+    "avtex_gram_l2_u8": [_p, _i64, _i64, _i64, _p, _i64, _i64, _int, _p, _i64, _p, _p, _int, _p],
+    "avtex_frame_norms_u8": [_p, _i64, _i64, _i64, _p, _p, _int, _p],
     "avtex_pairdist_direct_f32": [_p, _i64, _i64, _i64, _i64, _i64, _p, _i64, _p, _p, _int, _p],
     "avtex_pairdist_direct_u8": [_p, _i64, _i64, _i64, _i64, _i64, _p, _i64, _p, _p, _int, _p],
     "avtex_sum_nnz": [_p, _i64, _i64, _i64, _p, _p, _int, _p],
     "avtex_diag_filter_pow": [_p, _i64, _i64, _i64, C.POINTER(_f32), _int, _int, _i64, _i64, _i64,
                               _p, _i64, _p, _i64, _f32, _p, _p, _int, _p],
     "avtex_future_cost_sweep": [_p, _i64, _i64, _i64, _i64, _p, _p, _f32, _p, _p, _int, _p],
+    "avtex_future_cost_fused": [_p, _i64, _i64, _f32, _f32, _int, _p, _i64, _p, _p, _int, _p],
     "avtex_future_cost_finalize": [_p, _i64, _i64, _i64, _i64, _p, _f32, _p, _i64, _p, _p, _int, _p],
     "avtex_transition_probs": [_p, _i64, _i64, _i64, _f32, _int, _i64, _p, _i64, _f32, _p, _i64, _p, _int, _p],
     "avtex_row_nnz": [_p, _i64, _i64, _i64, _p, _int, _p],

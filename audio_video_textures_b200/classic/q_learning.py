@@ -27,7 +27,7 @@ def q_learning(
         D2 = D2.contiguous()
     # D3 = D2 ** p through the filter kernel's fused pow with the identity tap (fs = 1, stride 1)
     _, D3 = engine.diag_filter(D2, 1, 1, p=p, taps=[1.0])
-    fc = engine.future_cost(D3, alpha, verbose=True)
+    fc = engine.future_cost_fused(D3, alpha, verbose=True)
     stats = engine.new_stats(D2.device)
     D3_new = engine.future_cost_finalize(D3, fc.mvec, alpha, stats=stats)
     P3, P3_new, sigma, counts = tail(D3_new, sigma_factor, stats, threshold=thresholding)

@@ -11,10 +11,13 @@
 //
 // fl(alpha*m) and the add are written with __fmul_rn / __fadd_rn: nvcc must not contract them into
 // an FMA, the reference rounds twice (`alpha * mins`, then `D3[i] + ...`).
+#include <cooperative_groups.h>
 #include <float.h>
 #include <math.h>
 
 #include "common.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace {
 
@@ -45,8 +48,10 @@ __device__ __forceinline__ void sweep_vec4(const float4 v, const float *__restri
                                            const float *__restrict__ mp2, int64_t k, int64_t j, float alpha,
                                            SweepAcc &acc) {
     float4 a = make_float4(0.f, 0.f, 0.f, 0.f), a2 = a;
-    if (USE_A) a = *reinterpret_cast<const float4 *>(mp + k);
-    if (EPS && HAVE2) a2 = *reinterpret_cast<const float4 *>(mp2 + k);
+    // ld.global.cg: the m vectors are rewritten between sweeps by other CTAs of the fused kernel, so they
+    // must come from L2, never from the non-coherent / L1 path
+    if (USE_A) a = __ldcg(reinterpret_cast<const float4 *>(mp + k));
+    if (EPS && HAVE2) a2 = __ldcg(reinterpret_cast<const float4 *>(mp2 + k));
     sweep_elem<USE_A, EPS, HAVE2>(v.x, a.x, a2.x, k + 0, j, alpha, acc);
     sweep_elem<USE_A, EPS, HAVE2>(v.y, a.y, a2.y, k + 1, j, alpha, acc);
     sweep_elem<USE_A, EPS, HAVE2>(v.z, a.z, a2.z, k + 2, j, alpha, acc);
@@ -71,7 +76,7 @@ __device__ __forceinline__ void sweep_row(const float *__restrict__ row, int64_t
     }
     for (; k < mv; k += ST * 4) sweep_vec4<USE_A, EPS, HAVE2>(ld_stream_f4(row + k), mp, mp2, k, j, alpha, acc);
     for (int64_t s = mv + threadIdx.x; s < m; s += ST)
-        sweep_elem<USE_A, EPS, HAVE2>(row[s], USE_A ? mp[s] : 0.f, (EPS && HAVE2) ? mp2[s] : 0.f, s, j, alpha, acc);
+        sweep_elem<USE_A, EPS, HAVE2>(row[s], USE_A ? __ldcg(mp + s) : 0.f, (EPS && HAVE2) ? __ldcg(mp2 + s) : 0.f, s, j, alpha, acc);
 }
 
 __global__ void __launch_bounds__(ST)
@@ -144,6 +149,55 @@ future_cost_finalize_kernel(const float *__restrict__ D3, int64_t ld, int64_t ro
     }
 }
 
+// All sweeps in one cooperative launch: persistent CTAs stride over the rows, a grid barrier separates
+// the sweeps, and every CTA evaluates the reference's stop rule from the same fp64 numerator.
+// At M = 1241 (D3 = 6 MB, L2-resident) a sweep is ~5 us of work; the per-sweep launch + host read of
+// eps it replaces cost ~25 us each.
+__global__ void __launch_bounds__(ST)
+future_cost_fused_kernel(const float *__restrict__ D3, int64_t ld, int64_t m, float alpha, float eps_stop,
+                         int max_sweeps, float *mbuf, int64_t mpad, double *eps_trail, int *info) {
+    __shared__ float fred[32];
+    __shared__ double dred[32];
+    cg::grid_group grid = cg::this_grid();
+    float *buf[3] = {mbuf, mbuf + mpad, mbuf + 2 * mpad};
+    // pass 0: m^0 = off-diagonal row minima of D3
+    for (int64_t j = blockIdx.x; j < m; j += gridDim.x) {
+        SweepAcc acc{INFINITY, 0.0};
+        sweep_row<false, false, false>(D3 + j * ld, m, j, nullptr, nullptr, alpha, acc);
+        const float mn = block_reduce(acc.mn, INFINITY, OpMin(), fred);
+        if (threadIdx.x == 0) buf[0][j] = mn;
+    }
+    grid.sync();
+    int cur = 0, prev2 = -1;
+    for (int p = 1; p <= max_sweeps; ++p) {
+        const int out = 3 - cur - (prev2 < 0 ? (cur == 0 ? 1 : 0) : prev2);      // the buffer that is neither cur nor prev2
+        const float *mp = buf[cur];
+        const float *mp2 = prev2 < 0 ? nullptr : buf[prev2];
+        double e_blk = 0.0;
+        for (int64_t j = blockIdx.x; j < m; j += gridDim.x) {
+            SweepAcc acc{INFINITY, 0.0};
+            const float *row = D3 + j * ld;
+            if (j == 0) sweep_row<false, false, false>(row, m, j, mp, mp2, alpha, acc);
+            else if (mp2 == nullptr) sweep_row<true, true, false>(row, m, j, mp, mp2, alpha, acc);
+            else sweep_row<true, true, true>(row, m, j, mp, mp2, alpha, acc);
+            const float mn = block_reduce(acc.mn, INFINITY, OpMin(), fred);
+            if (threadIdx.x == 0) buf[out][j] = mn;
+            e_blk += block_reduce(acc.e, 0.0, OpAdd<double>(), dred);
+        }
+        if (threadIdx.x == 0 && e_blk != 0.0) atomicAdd(eps_trail + p, e_blk);
+        grid.sync();
+        const double num = *reinterpret_cast<volatile double *>(eps_trail + p);
+        const float eps = (float)(num / ((double)m * (double)m));
+        if (!(eps > eps_stop)) {
+            if (blockIdx.x == 0 && threadIdx.x == 0) { info[0] = p; info[1] = cur; }
+            return;
+        }
+        prev2 = cur;
+        cur = out;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) { info[0] = 0; info[1] = cur; }
+}
+
 }  // namespace
 
 extern "C" int avtex_future_cost_sweep(const float *D3, int64_t ld, int64_t row0, int64_t rows, int64_t m,
@@ -176,5 +230,28 @@ extern "C" int avtex_future_cost_finalize(const float *D3, int64_t ld, int64_t r
     future_cost_finalize_kernel<<<(unsigned)rows, ST, 0, as_stream(stream)>>>(D3, ld, row0, m, mvec, alpha,
                                                                               D3_new, ld_out, sum, nnz);
     AVTEX_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int avtex_future_cost_fused(const float *D3, int64_t ld, int64_t m, float alpha, float eps_stop,
+                                       int max_sweeps, float *mbuf, int64_t mpad, double *eps_trail, int *info,
+                                       int device, void *stream) {
+    AVTEX_ENTER(device);
+    AVTEX_REQUIRE(m >= 2 && ld >= m && mpad >= m && mpad % 4 == 0 && max_sweeps >= 1,
+                  "future_cost_fused: bad shape m=%lld ld=%lld mpad=%lld", (long long)m, (long long)ld, (long long)mpad);
+    AVTEX_REQUIRE((reinterpret_cast<uintptr_t>(mbuf) & 15) == 0, "future_cost_fused: mbuf must be 16-byte aligned");
+    int sms = 0, cc = 0, per_sm = 0, coop = 0;
+    if (int rc = avtex_device_info(device, &sms, &cc)) return rc;
+    AVTEX_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device));
+    AVTEX_REQUIRE(coop != 0, "future_cost_fused: device does not support cooperative launch");
+    AVTEX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, future_cost_fused_kernel, ST, 0));
+    AVTEX_REQUIRE(per_sm >= 1, "future_cost_fused: kernel does not fit on an SM");
+    if (per_sm > 4) per_sm = 4;
+    int64_t grid = (int64_t)sms * per_sm;
+    if (grid > m) grid = m;
+    void *args[] = {(void *)&D3, (void *)&ld, (void *)&m, (void *)&alpha, (void *)&eps_stop, (void *)&max_sweeps,
+                    (void *)&mbuf, (void *)&mpad, (void *)&eps_trail, (void *)&info};
+    AVTEX_CUDA(cudaLaunchCooperativeKernel((void *)future_cost_fused_kernel, dim3((unsigned)grid), dim3(ST), args, 0,
+                                           as_stream(stream)));
     return 0;
 }

@@ -44,8 +44,11 @@ constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*b
 // kind::i8 instruction descriptor (cute/arch/mma_sm100_desc.hpp bit layout):
 //   c_format[4,6)=2 (S32) | a_format[7,10)=1 (s8) | b_format[10,13)=1 (s8) | a/b major = K (0)
 //   n_dim[17,23) = N>>3 | m_dim[24,29) = M>>4
-constexpr uint32_t IDESC_S8 = (2u << 4) | (1u << 7) | (1u << 10) | (uint32_t(BN >> 3) << 17) |
-                              (uint32_t(BM >> 4) << 24);
+//   a_format / b_format: 1 = signed 8-bit (centred frames from pack.cu), 0 = unsigned (raw frames)
+constexpr uint32_t make_idesc(int m, bool is_signed) {
+    return (2u << 4) | ((is_signed ? 1u : 0u) << 7) | ((is_signed ? 1u : 0u) << 10) | (uint32_t(BN >> 3) << 17) |
+           (uint32_t(m >> 4) << 24);
+}
 
 struct GramArgs {
     int64_t n, kp, row0, rows, ldd;
@@ -54,6 +57,7 @@ struct GramArgs {
     double *sum;
     unsigned long long *nnz;
     int symmetric, TM, TN, num_tiles;
+    uint32_t idesc;                     // kind::i8 instruction descriptor (signed or unsigned operands)
 };
 
 // ------------------------------------------------------------------ PTX wrappers
@@ -299,7 +303,7 @@ gram_l2_s8_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     uint32_t *tmem_slot_ptr = reinterpret_cast<uint32_t *>(smem_raw + (tmem_slot - raw));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int KB = int(args.kp / BKB);
+    const int KB = int((args.kp + BKB - 1) / BKB);
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
@@ -350,7 +354,7 @@ gram_l2_s8_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
 #pragma unroll
                     for (int k = 0; k < BKB / UMMA_KB; ++k)
                         umma_s8(d_tmem, da + uint64_t(k * (UMMA_KB >> 4)), db + uint64_t(k * (UMMA_KB >> 4)),
-                                IDESC_S8, (kb | k) != 0);
+                                args.idesc, (kb | k) != 0);
                     umma_commit(empty_bar + 8 * stage);                   // frees the smem stage when the MMAs retire
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
@@ -395,8 +399,6 @@ constexpr int STAGES2 = 6;
 constexpr int STAGE2_BYTES = 2 * A_BYTES;             // A half (128 rows) + B half (128 rows)
 constexpr int GROUP_M2 = 8;
 constexpr int SMEM2_BYTES = STAGES2 * STAGE2_BYTES + 1024 + 256 + EPI_SMEM_BYTES;
-constexpr uint32_t IDESC_S8_2CTA = (2u << 4) | (1u << 7) | (1u << 10) | (uint32_t(BN >> 3) << 17) |
-                                   (uint32_t(BM2 >> 4) << 24);
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
     uint32_t r;
@@ -508,7 +510,7 @@ gram_l2_s8_2cta_kernel(const __grid_constant__ CUtensorMap map, const GramArgs a
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
     const bool leader = (rank == 0);
-    const int KB = int(args.kp / BKB);
+    const int KB = int((args.kp + BKB - 1) / BKB);
     const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
 
     if (warp == 0 && lane == 0) {
@@ -563,7 +565,7 @@ gram_l2_s8_2cta_kernel(const __grid_constant__ CUtensorMap map, const GramArgs a
 #pragma unroll
                     for (int k = 0; k < BKB / UMMA_KB; ++k)
                         umma_s8_2cta(d_tmem, da + uint64_t(k * (UMMA_KB >> 4)), db + uint64_t(k * (UMMA_KB >> 4)),
-                                     IDESC_S8_2CTA, (kb | k) != 0);
+                                     args.idesc, (kb | k) != 0);
                     umma_commit_2cta(empty_bar + 8 * stage);              // frees the stage in both CTAs
                     if (++stage == STAGES2) { stage = 0; phase ^= 1; }
                 }
@@ -616,9 +618,10 @@ int get_encode_fn(EncodeTiledFn *out) {
     return 0;
 }
 
-int make_map(EncodeTiledFn enc, CUtensorMap *map, const void *base, int64_t n, int64_t kp, int box_rows) {
-    const cuuint64_t gdim[2] = {(cuuint64_t)kp, (cuuint64_t)n};
-    const cuuint64_t gstride[1] = {(cuuint64_t)kp};
+int make_map(EncodeTiledFn enc, CUtensorMap *map, const void *base, int64_t n, int64_t k_extent, int64_t pitch,
+             int box_rows) {
+    const cuuint64_t gdim[2] = {(cuuint64_t)k_extent, (cuuint64_t)n};       // columns beyond k_extent read as 0
+    const cuuint64_t gstride[1] = {(cuuint64_t)pitch};
     const cuuint32_t box[2] = {(cuuint32_t)BKB, (cuuint32_t)box_rows};
     const cuuint32_t estr[2] = {1, 1};
     const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void *>(base), gdim, gstride, box, estr,
@@ -628,39 +631,37 @@ int make_map(EncodeTiledFn enc, CUtensorMap *map, const void *base, int64_t n, i
     return 0;
 }
 
-}  // namespace
-
-extern "C" int avtex_gram_l2_s8(const int8_t *packed, int64_t n, int64_t kp, const int64_t *sqnorm,
-                                int64_t row0, int64_t rows, int symmetric, float *D, int64_t ldd,
-                                double *sum, unsigned long long *nnz, int device, void *stream) {
+int launch_gram(const void *operand, bool is_signed, int64_t n, int64_t k_extent, int64_t pitch, const int64_t *sqnorm,
+                int64_t row0, int64_t rows, int symmetric, float *D, int64_t ldd, double *sum, unsigned long long *nnz,
+                int device, void *stream) {
     AVTEX_ENTER(device);
-    AVTEX_REQUIRE(n >= 1 && n < (int64_t(1) << 30) && kp >= BKB && kp % BKB == 0 && kp < (int64_t(1) << 31),
-                  "gram_l2_s8: bad shape n=%lld kp=%lld", (long long)n, (long long)kp);
-    AVTEX_REQUIRE(rows >= 1 && row0 >= 0 && row0 + rows <= n && ldd >= n, "gram_l2_s8: bad row block [%lld,+%lld)",
+    AVTEX_REQUIRE(n >= 1 && n < (int64_t(1) << 30) && k_extent >= 1 && k_extent < (int64_t(1) << 31),
+                  "gram_l2: bad shape n=%lld k=%lld", (long long)n, (long long)k_extent);
+    AVTEX_REQUIRE(pitch >= k_extent && pitch % 16 == 0 && (reinterpret_cast<uintptr_t>(operand) & 15) == 0,
+                  "gram_l2: operand rows must be 16-byte aligned (pitch %lld)", (long long)pitch);
+    AVTEX_REQUIRE(rows >= 1 && row0 >= 0 && row0 + rows <= n && ldd >= n, "gram_l2: bad row block [%lld,+%lld)",
                   (long long)row0, (long long)rows);
-    AVTEX_REQUIRE(!symmetric || (row0 == 0 && rows == n), "gram_l2_s8: symmetric mode needs the full matrix");
-    AVTEX_REQUIRE((reinterpret_cast<uintptr_t>(packed) & 127) == 0, "gram_l2_s8: packed must be 128-byte aligned");
-    AVTEX_REQUIRE((sum == nullptr) == (nnz == nullptr), "gram_l2_s8: sum and nnz go together");
+    AVTEX_REQUIRE(!symmetric || (row0 == 0 && rows == n), "gram_l2: symmetric mode needs the full matrix");
+    AVTEX_REQUIRE((sum == nullptr) == (nnz == nullptr), "gram_l2: sum and nnz go together");
     int cc = 0, sms = 0;
     if (int rc = avtex_device_info(device, &sms, &cc)) return rc;
-    AVTEX_REQUIRE(cc == 100, "gram_l2_s8: needs an sm_100 device (tcgen05 kind::i8), got cc %d", cc);
+    AVTEX_REQUIRE(cc == 100, "gram_l2: needs an sm_100 device (tcgen05 kind::i8), got cc %d", cc);
 
     EncodeTiledFn enc;
     if (int rc = get_encode_fn(&enc)) return rc;
-    CUtensorMap map_a, map_b;
-    if (int rc = make_map(enc, &map_a, packed, n, kp, BM)) return rc;
-    if (int rc = make_map(enc, &map_b, packed, n, kp, BN)) return rc;
-
     GramArgs a;
-    a.n = n; a.kp = kp; a.row0 = row0; a.rows = rows; a.ldd = ldd;
+    a.n = n; a.kp = k_extent; a.row0 = row0; a.rows = rows; a.ldd = ldd;
     a.sqnorm = sqnorm; a.D = D; a.sum = sum; a.nnz = nnz;
     a.symmetric = symmetric ? 1 : 0;
     const char *mode = getenv("AVTEX_GRAM_MODE");                  // "1cta" selects the single-CTA kernel
     const bool two_cta = !(mode != nullptr && mode[0] == '1');
     if (two_cta) {
+        CUtensorMap map;
+        if (int rc = make_map(enc, &map, operand, n, k_extent, pitch, BM)) return rc;
         a.TM = int((rows + BM2 - 1) / BM2);
         a.TN = int((n + BN - 1) / BN);
         a.num_tiles = count_tiles2(a.TM, a.TN, a.symmetric);
+        a.idesc = make_idesc(BM2, is_signed);
         static bool attr2_set[64] = {false};
         if (device < 64 && !attr2_set[device]) {
             AVTEX_CUDA(cudaFuncSetAttribute(gram_l2_s8_2cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES));
@@ -668,13 +669,17 @@ extern "C" int avtex_gram_l2_s8(const int8_t *packed, int64_t n, int64_t kp, con
         }
         int clusters = sms / 2;
         if (a.num_tiles < clusters) clusters = a.num_tiles;
-        gram_l2_s8_2cta_kernel<<<2 * clusters, NUM_THREADS, SMEM2_BYTES, as_stream(stream)>>>(map_a, a);
+        gram_l2_s8_2cta_kernel<<<2 * clusters, NUM_THREADS, SMEM2_BYTES, as_stream(stream)>>>(map, a);
         AVTEX_LAUNCH_CHECK();
         return 0;
     }
+    CUtensorMap map_a, map_b;
+    if (int rc = make_map(enc, &map_a, operand, n, k_extent, pitch, BM)) return rc;
+    if (int rc = make_map(enc, &map_b, operand, n, k_extent, pitch, BN)) return rc;
     a.TM = int((rows + BM - 1) / BM);
     a.TN = int((n + BN - 1) / BN);
     a.num_tiles = count_tiles(a.TM, a.TN, a.symmetric);
+    a.idesc = make_idesc(BM, is_signed);
     static bool attr_set[64] = {false};
     if (device < 64 && !attr_set[device]) {
         AVTEX_CUDA(cudaFuncSetAttribute(gram_l2_s8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
@@ -684,6 +689,20 @@ extern "C" int avtex_gram_l2_s8(const int8_t *packed, int64_t n, int64_t kp, con
     gram_l2_s8_kernel<<<grid, NUM_THREADS, SMEM_BYTES, as_stream(stream)>>>(map_a, map_b, a);
     AVTEX_LAUNCH_CHECK();
     return 0;
+}
+
+}  // namespace
+
+extern "C" int avtex_gram_l2_s8(const int8_t *packed, int64_t n, int64_t kp, const int64_t *sqnorm,
+                                int64_t row0, int64_t rows, int symmetric, float *D, int64_t ldd,
+                                double *sum, unsigned long long *nnz, int device, void *stream) {
+    return launch_gram(packed, true, n, kp, kp, sqnorm, row0, rows, symmetric, D, ldd, sum, nnz, device, stream);
+}
+
+extern "C" int avtex_gram_l2_u8(const uint8_t *frames, int64_t n, int64_t k, int64_t ld, const int64_t *sqnorm,
+                                int64_t row0, int64_t rows, int symmetric, float *D, int64_t ldd,
+                                double *sum, unsigned long long *nnz, int device, void *stream) {
+    return launch_gram(frames, false, n, k, ld, sqnorm, row0, rows, symmetric, D, ldd, sum, nnz, device, stream);
 }
 
 extern "C" int avtex_gram_tile_schedule2(int TM, int TN, int symmetric, int *tm_out, int *tn_out, int capacity) {

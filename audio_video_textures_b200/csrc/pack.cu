@@ -18,7 +18,7 @@ __device__ __forceinline__ int sq4(unsigned int w) {            // sum of square
 
 __global__ void __launch_bounds__(PACK_THREADS)
 pack_u8_kernel(const uint8_t *__restrict__ in, int64_t k, int64_t ld, int8_t *__restrict__ out,
-               int64_t kp, int64_t *__restrict__ sqnorm) {
+               int64_t kp, int64_t *__restrict__ sqnorm, unsigned long long *__restrict__ max_sqnorm) {
     __shared__ unsigned long long scratch[32];
     const int64_t row = blockIdx.x;
     const uint8_t *src = in + row * ld;
@@ -37,12 +37,16 @@ pack_u8_kernel(const uint8_t *__restrict__ in, int64_t k, int64_t ld, int8_t *__
         dst[c] = (int8_t)v;
     }
     acc = block_reduce(acc, 0ull, OpAdd<unsigned long long>(), scratch);
-    if (threadIdx.x == 0) sqnorm[row] = (int64_t)acc;
+    if (threadIdx.x == 0) {
+        sqnorm[row] = (int64_t)acc;
+        if (max_sqnorm != nullptr) atomicMax(max_sqnorm, acc);
+    }
 }
 
 __global__ void __launch_bounds__(PACK_THREADS)
 pack_f32_kernel(const float *__restrict__ in, int64_t k, int64_t ld, int8_t *__restrict__ out,
-                int64_t kp, int64_t *__restrict__ sqnorm, int *__restrict__ flags) {
+                int64_t kp, int64_t *__restrict__ sqnorm, int *__restrict__ flags,
+                unsigned long long *__restrict__ max_sqnorm) {
     __shared__ unsigned long long scratch[32];
     const int64_t row = blockIdx.x;
     const float *src = in + row * ld;
@@ -81,8 +85,45 @@ pack_f32_kernel(const float *__restrict__ in, int64_t k, int64_t ld, int8_t *__r
         dst[c] = (int8_t)v;
     }
     acc = block_reduce(acc, 0ull, OpAdd<unsigned long long>(), scratch);
-    if (threadIdx.x == 0) sqnorm[row] = (int64_t)acc;
+    if (threadIdx.x == 0) {
+        sqnorm[row] = (int64_t)acc;
+        if (max_sqnorm != nullptr) atomicMax(max_sqnorm, acc);
+    }
     if (__syncthreads_or(bad) && threadIdx.x == 0) atomicOr(flags, 1);
+}
+
+// Norms only (no packed copy): the Gram kernel can contract the raw unsigned bytes directly
+// (kind::i8 with unsigned operands, see gram.cu), which needs sum x^2 per frame for the epilogue and the
+// CENTRED norm sum (x-128)^2 = sum x^2 - 256 sum x + 128^2 k for the d^2 < 2^32 domain guard.
+__global__ void __launch_bounds__(PACK_THREADS)
+frame_norms_u8_kernel(const uint8_t *__restrict__ in, int64_t k, int64_t ld, int64_t *__restrict__ sqnorm,
+                      unsigned long long *__restrict__ max_centred) {
+    __shared__ unsigned long long scratch[32];
+    const int64_t row = blockIdx.x;
+    const uint8_t *src = in + row * ld;
+    unsigned long long sq = 0, sm = 0;
+    const bool vec = ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
+    const int64_t kv = vec ? (k & ~int64_t(15)) : 0;
+    for (int64_t c = int64_t(threadIdx.x) * 16; c < kv; c += int64_t(PACK_THREADS) * 16) {
+        const uint4 v = __ldg(reinterpret_cast<const uint4 *>(src + c));
+        unsigned int q = 0, t = 0;
+        q = __dp4a(v.x, v.x, q); q = __dp4a(v.y, v.y, q); q = __dp4a(v.z, v.z, q); q = __dp4a(v.w, v.w, q);
+        t = __dp4a(v.x, 0x01010101u, t); t = __dp4a(v.y, 0x01010101u, t);
+        t = __dp4a(v.z, 0x01010101u, t); t = __dp4a(v.w, 0x01010101u, t);
+        sq += q;
+        sm += t;
+    }
+    for (int64_t c = kv + threadIdx.x; c < k; c += PACK_THREADS) {
+        const unsigned int v = src[c];
+        sq += v * v;
+        sm += v;
+    }
+    sq = block_reduce(sq, 0ull, OpAdd<unsigned long long>(), scratch);
+    sm = block_reduce(sm, 0ull, OpAdd<unsigned long long>(), scratch);
+    if (threadIdx.x == 0) {
+        sqnorm[row] = (int64_t)sq;
+        if (max_centred != nullptr) atomicMax(max_centred, sq + 16384ull * (unsigned long long)k - 256ull * sm);
+    }
 }
 
 }  // namespace
@@ -97,22 +138,32 @@ static int check_pack(int64_t n, int64_t k, int64_t ld, int64_t kp) {
 }
 
 extern "C" int avtex_pack_frames_u8(const uint8_t *frames, int64_t n, int64_t k, int64_t ld,
-                                    int8_t *packed, int64_t kp, int64_t *sqnorm, int device,
-                                    void *stream) {
+                                    int8_t *packed, int64_t kp, int64_t *sqnorm,
+                                    unsigned long long *max_sqnorm, int device, void *stream) {
     AVTEX_ENTER(device);
     if (int rc = check_pack(n, k, ld, kp)) return rc;
-    pack_u8_kernel<<<(unsigned)n, PACK_THREADS, 0, as_stream(stream)>>>(frames, k, ld, packed, kp, sqnorm);
+    pack_u8_kernel<<<(unsigned)n, PACK_THREADS, 0, as_stream(stream)>>>(frames, k, ld, packed, kp, sqnorm, max_sqnorm);
     AVTEX_LAUNCH_CHECK();
     return 0;
 }
 
 extern "C" int avtex_pack_frames_f32(const float *frames, int64_t n, int64_t k, int64_t ld,
                                      int8_t *packed, int64_t kp, int64_t *sqnorm, int *flags,
-                                     int device, void *stream) {
+                                     unsigned long long *max_sqnorm, int device, void *stream) {
     AVTEX_ENTER(device);
     if (int rc = check_pack(n, k, ld, kp)) return rc;
     AVTEX_REQUIRE(flags != nullptr, "pack_frames_f32: flags must not be NULL");
-    pack_f32_kernel<<<(unsigned)n, PACK_THREADS, 0, as_stream(stream)>>>(frames, k, ld, packed, kp, sqnorm, flags);
+    pack_f32_kernel<<<(unsigned)n, PACK_THREADS, 0, as_stream(stream)>>>(frames, k, ld, packed, kp, sqnorm, flags, max_sqnorm);
+    AVTEX_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int avtex_frame_norms_u8(const uint8_t *frames, int64_t n, int64_t k, int64_t ld, int64_t *sqnorm,
+                                    unsigned long long *max_centred, int device, void *stream) {
+    AVTEX_ENTER(device);
+    AVTEX_REQUIRE(n > 0 && k > 0 && ld >= k && n < (int64_t(1) << 31), "frame_norms_u8: bad shape n=%lld k=%lld ld=%lld",
+                  (long long)n, (long long)k, (long long)ld);
+    frame_norms_u8_kernel<<<(unsigned)n, PACK_THREADS, 0, as_stream(stream)>>>(frames, k, ld, sqnorm, max_centred);
     AVTEX_LAUNCH_CHECK();
     return 0;
 }

@@ -77,44 +77,74 @@ def sum_nnz(D: torch.Tensor, stats: torch.Tensor | None = None) -> torch.Tensor:
 
 
 # --------------------------------------------------------------------------- K0 / K1
-@dataclass
-class PackedFrames:
-    packed: torch.Tensor          # [N, Kp] int8, centred
-    sqnorm: torch.Tensor          # [N] int64
-    k: int
-    exact_ok: bool                # False -> use the direct path
-    reason: str = ""
-
-
 GRAM_MAX_SQNORM = (1 << 32) // 4  # (sqrt(n_r)+sqrt(n_c))^2 <= 4 max(n) must stay below 2^32
 
 
+@dataclass
+class PackedFrames:
+    """Gram operand: either the raw uint8 frames themselves (`signed` False, no copy) or the centred
+    int8 copy written by K0 (`signed` True; float inputs, or byte rows that are not 16-byte aligned)."""
+    packed: torch.Tensor          # [N, K] uint8 (raw) or [N, Kp] int8 (centred, zero padded)
+    sqnorm: torch.Tensor          # [N] int64: sum x^2 of the operand rows
+    k: int
+    flags: torch.Tensor           # int64[2] on device: [non-byte values seen, max centred sqnorm]
+    signed: bool = True
+    _checked: tuple | None = None
+
+    def validate(self):
+        """(ok, reason): is the tensor-core Gram path exact for these frames?  One 16-byte D2H read,
+        deferred so that avtex_gram_l2_s8 can already be running (it is launched speculatively; its
+        result must be discarded when this returns False)."""
+        if self._checked is None:
+            bad, mx = (int(v) for v in self.flags.cpu())
+            if bad:
+                self._checked = (False, "frames are not integer-valued bytes")
+            elif mx >= GRAM_MAX_SQNORM:
+                self._checked = (False, "squared norms too large for the mod-2^32 epilogue")
+            else:
+                self._checked = (True, "")
+        return self._checked
+
+    @property
+    def exact_ok(self) -> bool:
+        return self.validate()[0]
+
+    @property
+    def reason(self) -> str:
+        return self.validate()[1]
+
+
 def pack_frames(frames: torch.Tensor) -> PackedFrames:
-    """K0.  frames: CUDA tensor [N, ...] uint8 or float (integer-valued 0..255)."""
+    """K0.  frames: CUDA tensor [N, ...] uint8 or float (integer-valued 0..255).  No host sync."""
     x = frames.reshape(frames.shape[0], -1)
     if x.stride(-1) != 1:
         x = x.contiguous()
     n, k = x.shape
     kp = (k + 127) // 128 * 128
-    packed = torch.empty((n, kp), dtype=torch.int8, device=x.device)
     sqnorm = torch.empty(n, dtype=torch.int64, device=x.device)
+    flags = torch.zeros(2, dtype=torch.int64, device=x.device)
     dev, st = _dev(x), _stream(x)
-    ok, reason = True, ""
+    mx = C.c_void_p(flags.data_ptr() + 8)
+    if x.dtype == torch.uint8 and x.stride(0) % 16 == 0 and x.data_ptr() % 16 == 0:
+        # raw bytes feed the tensor cores directly: only the norms are computed (one read of the frames)
+        _lib.call("avtex_frame_norms_u8", _lib.ptr(x), n, k, x.stride(0), _lib.ptr(sqnorm), mx, dev, st)
+        pf = PackedFrames(x, sqnorm, k, flags, signed=False)
+        if kp * 128 * 128 < GRAM_MAX_SQNORM:
+            pf._checked = (True, "")
+        return pf
+    packed = torch.empty((n, kp), dtype=torch.int8, device=x.device)
     if x.dtype == torch.uint8:
         _lib.call("avtex_pack_frames_u8", _lib.ptr(x), n, k, x.stride(0), _lib.ptr(packed), kp,
-                  _lib.ptr(sqnorm), dev, st)
+                  _lib.ptr(sqnorm), mx, dev, st)
     elif x.dtype == torch.float32:
-        flags = torch.zeros(1, dtype=torch.int32, device=x.device)
         _lib.call("avtex_pack_frames_f32", _lib.ptr(x), n, k, x.stride(0), _lib.ptr(packed), kp,
-                  _lib.ptr(sqnorm), _lib.ptr(flags), dev, st)
-        if int(flags.item()) != 0:
-            ok, reason = False, "frames are not integer-valued bytes"
+                  _lib.ptr(sqnorm), _lib.ptr(flags), mx, dev, st)
     else:
         raise TypeError(f"frames dtype {x.dtype} not supported (uint8 or float32)")
-    if ok and kp * 128 * 128 >= GRAM_MAX_SQNORM:           # only then can a norm exceed the bound
-        if int(sqnorm.max().item()) >= GRAM_MAX_SQNORM:
-            ok, reason = False, "squared norms too large for the mod-2^32 epilogue"
-    return PackedFrames(packed, sqnorm, k, ok, reason)
+    pf = PackedFrames(packed, sqnorm, k, flags, signed=True)
+    if kp * 128 * 128 < GRAM_MAX_SQNORM and x.dtype == torch.uint8:
+        pf._checked = (True, "")                           # no byte frame of this size can leave the domain
+    return pf
 
 
 def gram_l2(pf: PackedFrames, row0: int = 0, rows: int | None = None, symmetric: bool | None = None,
@@ -126,8 +156,12 @@ def gram_l2(pf: PackedFrames, row0: int = 0, rows: int | None = None, symmetric:
         symmetric = (row0 == 0 and rows == n)
     D = empty_matrix(rows, n, pf.packed.device) if out is None else out
     s, z = _stats_ptrs(stats)
-    _lib.call("avtex_gram_l2_s8", _lib.ptr(pf.packed), n, kp, _lib.ptr(pf.sqnorm), row0, rows,
-              1 if symmetric else 0, _lib.ptr(D), D.stride(0), s, z, _dev(D), _stream(D))
+    if pf.signed:
+        _lib.call("avtex_gram_l2_s8", _lib.ptr(pf.packed), n, kp, _lib.ptr(pf.sqnorm), row0, rows,
+                  1 if symmetric else 0, _lib.ptr(D), D.stride(0), s, z, _dev(D), _stream(D))
+    else:
+        _lib.call("avtex_gram_l2_u8", _lib.ptr(pf.packed), n, pf.k, pf.packed.stride(0), _lib.ptr(pf.sqnorm),
+                  row0, rows, 1 if symmetric else 0, _lib.ptr(D), D.stride(0), s, z, _dev(D), _stream(D))
     return D
 
 
@@ -155,10 +189,13 @@ def pairwise_l2(frames: torch.Tensor, row0: int = 0, rows: int | None = None,
         raise ValueError(method)
     if method != "direct" and frames.dtype in (torch.uint8, torch.float32):
         pf = pack_frames(frames)
+        D = gram_l2(pf, row0, rows, stats=stats)           # speculative: validated right below
         if pf.exact_ok:
-            return gram_l2(pf, row0, rows, stats=stats), "gram"
+            return D, "gram"
         if method == "gram":
             raise _lib.AvtexError(f"gram path not applicable: {pf.reason}")
+        if stats is not None:
+            stats.zero_()
     return pairdist_direct(frames if frames.dtype == torch.uint8 else frames.float(), row0, rows, stats), "direct"
 
 
@@ -276,6 +313,27 @@ def future_cost(D3: torch.Tensor, alpha: float = 0.997, row0: int = 0, m: int | 
             free.append(prev2)
         prev2, cur = cur, out
     raise RuntimeError("future cost did not converge")
+
+
+def future_cost_fused(D3: torch.Tensor, alpha: float = 0.997, verbose: bool = False,
+                      max_sweeps: int = 4096) -> FutureCostResult:
+    """K3, all sweeps in one cooperative launch (single GPU): no host round trip per sweep."""
+    m = D3.shape[1]
+    mpad = (m + 31) // 32 * 32
+    mbuf = torch.zeros(3 * mpad, dtype=torch.float32, device=D3.device)
+    trail = torch.zeros(max_sweeps + 1, dtype=torch.float64, device=D3.device)
+    info = torch.zeros(2, dtype=torch.int32, device=D3.device)
+    _lib.call("avtex_future_cost_fused", _lib.ptr(D3), D3.stride(0), m, C.c_float(_f32(alpha)),
+              C.c_float(np.float32(F32_EPS_STOP)), max_sweeps, _lib.ptr(mbuf), mpad, _lib.ptr(trail),
+              _lib.ptr(info), _dev(D3), _stream(D3))
+    n_sweeps, idx = (int(v) for v in info.cpu())
+    if n_sweeps == 0:
+        raise RuntimeError("future cost did not converge")
+    eps = [float(np.float32(v / (float(m) * float(m)))) for v in trail[1:n_sweeps + 1].cpu()]
+    if verbose:
+        for e in eps:
+            print("Eps:", f"tensor({e:.4f}, device='{D3.device}')")
+    return FutureCostResult(mbuf[idx * mpad: idx * mpad + m], n_sweeps, eps, n_sweeps + 1)
 
 
 def future_cost_finalize(D3: torch.Tensor, mvec: torch.Tensor, alpha: float = 0.997, row0: int = 0,

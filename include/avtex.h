@@ -48,14 +48,17 @@ AVTEX_API int avtex_zero(void *ptr, int64_t bytes, int device, void *stream);
  * int32 tensor-core accumulator of avtex_gram_l2_s8 inside its range.
  * The f32 variant requires integer-valued inputs in [0, 255] (a uint8-derived video as float);
  * it sets flags[0] = 1 if any element is not, and the caller must then use
- * avtex_pairdist_direct_f32.
+ * avtex_pairdist_direct_f32.  max_sqnorm (nullable, zeroed by the caller) receives max_i sqnorm[i]
+ * (atomicMax), so the host can launch avtex_gram_l2_s8 speculatively and validate its domain
+ * (4 * max < 2^32) later with one small D2H read instead of a reduction + sync in between.
  * replaces: the operand staging of classic/computeD1.py:61-83 (`frames[i:i+bs].cuda()`, repeat, view).
  */
 AVTEX_API int avtex_pack_frames_u8(const uint8_t *frames, int64_t n, int64_t k, int64_t ld,
-                         int8_t *packed, int64_t kp, int64_t *sqnorm, int device, void *stream);
+                         int8_t *packed, int64_t kp, int64_t *sqnorm,
+                         unsigned long long *max_sqnorm, int device, void *stream);
 AVTEX_API int avtex_pack_frames_f32(const float *frames, int64_t n, int64_t k, int64_t ld,
                           int8_t *packed, int64_t kp, int64_t *sqnorm, int *flags,
-                          int device, void *stream);
+                          unsigned long long *max_sqnorm, int device, void *stream);
 
 /* ---------------------------------------------------------------- K1: pairwise L2 distances
  * D[(r - row0), j] = sqrt( sqnorm[r] + sqnorm[j] - 2 * <packed[r], packed[j]> ),  r in [row0, row0+rows),
@@ -70,6 +73,20 @@ AVTEX_API int avtex_pack_frames_f32(const float *frames, int64_t n, int64_t k, i
 AVTEX_API int avtex_gram_l2_s8(const int8_t *packed, int64_t n, int64_t kp, const int64_t *sqnorm,
                      int64_t row0, int64_t rows, int symmetric, float *D, int64_t ldd,
                      double *sum, unsigned long long *nnz, int device, void *stream);
+
+/* Same kernel on the RAW unsigned frames (no packed copy): frames [n, k] u8 with a row pitch `ld` that is
+ * a multiple of 16 bytes, sqnorm[i] = sum_c frames[i,c]^2 from avtex_frame_norms_u8.  u8 x u8 products
+ * are accumulated in the int32 TMEM accumulator modulo 2^32 (it wraps for typical video: sum x*y ~ 3e9 at
+ * K = 150528); together with the mod-2^32 epilogue the result is exact under the same precondition as
+ * above, which is stated on the CENTRED norms: 4 * max_i sum_c (frames[i,c]-128)^2 < 2^32
+ * (avtex_frame_norms_u8 returns that maximum).  K is not padded: TMA zero-fills columns >= k. */
+AVTEX_API int avtex_gram_l2_u8(const uint8_t *frames, int64_t n, int64_t k, int64_t ld, const int64_t *sqnorm,
+                     int64_t row0, int64_t rows, int symmetric, float *D, int64_t ldd,
+                     double *sum, unsigned long long *nnz, int device, void *stream);
+/* sqnorm[i] = sum_c frames[i,c]^2 (exact); max_centred (nullable, zeroed by the caller) receives
+ * max_i sum_c (frames[i,c]-128)^2 via atomicMax.  HBM-bound: one read of the frames. */
+AVTEX_API int avtex_frame_norms_u8(const uint8_t *frames, int64_t n, int64_t k, int64_t ld, int64_t *sqnorm,
+                         unsigned long long *max_centred, int device, void *stream);
 
 /* Same contract by direct difference in fp32 (the reference's own formula), for arbitrary float
  * features; SIMT, no tensor cores.  x is [n, k] fp32. */
@@ -115,6 +132,16 @@ AVTEX_API int avtex_diag_filter_pow(const float *D1, int64_t ld1, int64_t in_row
 AVTEX_API int avtex_future_cost_sweep(const float *D3, int64_t ld, int64_t row0, int64_t rows, int64_t m,
                             const float *m_prev, const float *m_prev2, float alpha,
                             float *m_new, double *eps_sum, int device, void *stream);
+/* All sweeps in ONE cooperative launch (single GPU): the same arithmetic as repeated
+ * avtex_future_cost_sweep calls, with a grid-wide barrier between sweeps and the stop rule
+ * `eps > eps_stop` evaluated on the device, so the host reads nothing until the end.
+ * mbuf: 3 * mpad floats (mpad >= m, multiple of 4; scratch, rotated).  eps_trail: max_sweeps+1 doubles,
+ * ZEROED by the caller; eps_trail[p] receives the numerator of sweep p.  info[0] = number of sweeps
+ * (0 if max_sweeps was exhausted), info[1] = index (0..2) of the buffer in mbuf holding the vector m with
+ * D3_new = D3 + fl(alpha*m).  replaces: classic/q_learning.py:39-51 including the while condition. */
+AVTEX_API int avtex_future_cost_fused(const float *D3, int64_t ld, int64_t m, float alpha, float eps_stop,
+                            int max_sweeps, float *mbuf, int64_t mpad, double *eps_trail, int *info,
+                            int device, void *stream);
 /* D3_new[j,:] = D3[j,:] + fl(alpha * mvec)  (j >= 1),  row 0 copied.  sum/nnz nullable.
  * replaces: the materialised D3_new of classic/q_learning.py:48 at convergence. */
 AVTEX_API int avtex_future_cost_finalize(const float *D3, int64_t ld, int64_t row0, int64_t rows, int64_t m,

@@ -51,8 +51,13 @@ def test_pack_frames_exact(eng, name):
     g = load_golden(name)
     video = torch.from_numpy(g["video"])
     x = video.reshape(video.shape[0], -1)
-    pf = eng.pack_frames(video.cuda())
-    assert pf.exact_ok
+    raw = eng.pack_frames(video.cuda())
+    assert raw.exact_ok and not raw.signed and raw.packed.dtype == torch.uint8          # bytes used as they are
+    assert torch.equal(raw.sqnorm.cpu(), (x.to(torch.int64) ** 2).sum(1))
+    mis = torch.empty(x.shape[0], x.shape[1] + 1, dtype=torch.uint8, device="cuda")[:, :x.shape[1]]
+    mis.copy_(x)                                                                       # pitch not 16-byte aligned
+    pf = eng.pack_frames(mis)
+    assert pf.exact_ok and pf.signed
     ref = (x.to(torch.int16) - 128).to(torch.int8)
     assert torch.equal(pf.packed[:, :x.shape[1]].cpu(), ref)
     assert int(pf.packed[:, x.shape[1]:].abs().sum()) == 0
@@ -83,6 +88,10 @@ def test_gram_distance_exact_and_within_tolerance(eng, name):
     total, nnz = eng.read_stats(stats)
     assert nnz == int((Dh != 0).sum())
     np.testing.assert_allclose(total, Dh.double().sum().item(), rtol=2e-7)   # fp32 partials per 32-chunk
+    # centred-int8 operand path (float frames) gives the identical matrix
+    pf8 = eng.pack_frames(video.float().cuda())
+    assert pf8.signed and not pf.signed
+    assert torch.equal(eng.gram_l2(pf8).cpu(), Dh)
     # row-block (non-symmetric) mode reproduces the same values: what a row shard computes
     n = video.shape[0]
     r0, rows = n // 3, n // 2
@@ -102,12 +111,13 @@ def test_gram_edge_shapes(eng):
         x = torch.randint(0, 256, (n, k), dtype=torch.uint8, generator=gen)
         if n > 5:
             x[5] = x[2]                        # duplicate -> exact zero off the diagonal
-        pf = eng.pack_frames(x.cuda())
-        D = eng.gram_l2(pf).cpu()
         exact = classic.pairwise_l2_exact_u8(x)
-        np.testing.assert_allclose(D.numpy(), exact.numpy(), rtol=2e-7)
-        if n > 5:
-            assert D[5, 2] == 0 and D[2, 5] == 0
+        for frames in (x.cuda(), x.float().cuda()):          # raw-u8 operand (when aligned) and centred-s8 operand
+            pf = eng.pack_frames(frames)
+            D = eng.gram_l2(pf).cpu()
+            np.testing.assert_allclose(D.numpy(), exact.numpy(), rtol=2e-7)
+            if n > 5:
+                assert D[5, 2] == 0 and D[2, 5] == 0
 
 
 def test_gram_domain_guard_and_extreme_values(eng):
@@ -132,10 +142,13 @@ def test_gram_domain_guard_and_extreme_values(eng):
     y[0] = 128 + 84                                           # n = K*84^2 = 1.06e9: 4n just below 2^32
     y[1] = 128 + 80
     y[2] = 128 - 80
-    pf = eng.pack_frames(y.cuda())
-    assert pf.exact_ok
-    Dg = eng.gram_l2(pf).cpu()
-    np.testing.assert_allclose(Dg.numpy(), classic.pairwise_l2_exact_u8(y).numpy(), rtol=2e-7)
+    for frames in (y.cuda(), y.float().cuda()):
+        # raw-u8 operand: <y0,y1> = K*212*208 = 6.6e9 wraps the int32 accumulator (mod 2^32) and must
+        # still give the exact distance; centred-s8 operand: no wrap
+        pf = eng.pack_frames(frames)
+        assert pf.exact_ok
+        Dg = eng.gram_l2(pf).cpu()
+        np.testing.assert_allclose(Dg.numpy(), classic.pairwise_l2_exact_u8(y).numpy(), rtol=2e-7)
 
 
 # ----------------------------------------------------------------------------- K2
@@ -208,6 +221,10 @@ def test_future_cost_bit_exact(eng, name):
     np.testing.assert_allclose(fc.eps_trail, trail, rtol=1e-5, atol=1e-12)
     for e in fc.eps_trail:                                     # stop decision is not marginal
         assert abs(e - 0.01) / 0.01 > 1e-3
+    # all sweeps in one cooperative launch: same vector, same sweep count, same eps trail
+    ff = eng.future_cost_fused(D3.cuda())
+    assert ff.n_sweeps == fc.n_sweeps and torch.equal(ff.mvec, fc.mvec[:ff.mvec.shape[0]])
+    np.testing.assert_allclose(ff.eps_trail, trail, rtol=1e-5, atol=1e-12)
     total, nnz = eng.read_stats(stats)
     sigma = eng.sigma_from_stats(total, nnz, g["sigma_factor"])
     np.testing.assert_allclose(sigma, g["ref_sigma3"], rtol=1e-6)
@@ -225,6 +242,8 @@ def test_future_cost_wide_rows(eng):
     assert fc.n_sweeps == len(trail)
     assert torch.equal(eng.future_cost_finalize(d, fc.mvec).cpu(), want)
     np.testing.assert_allclose(fc.eps_trail, trail, rtol=1e-5, atol=1e-12)
+    ff = eng.future_cost_fused(d)
+    assert ff.n_sweeps == len(trail) and torch.equal(eng.future_cost_finalize(d, ff.mvec).cpu(), want)
     # probabilities at the same width: shared-memory row cache path vs torch
     sigma = np.float32(25.0)
     P, Pn, counts = eng.transition_probs(d, sigma, threshold=0.08, want_counts=True)
