@@ -46,6 +46,16 @@ SIGNATURES = {
     "avtex_gram_tile_schedule2": [_int, _int, _int, C.POINTER(_int), C.POINTER(_int), _int],
 }
 
+class GramJob(C.Structure):
+    """Mirror of `AvtexGramJob` (include/avtex.h)."""
+    _fields_ = [("row0", _i64), ("rows", _i64), ("col0", _i64), ("cols", _i64),
+                ("D", _p), ("d_row0", _i64), ("ldd", _i64),
+                ("DT", _p), ("dt_row0", _i64), ("ldt", _i64),
+                ("symmetric", _int), ("count_stats", _int)]
+
+
+SIGNATURES["avtex_gram_l2_jobs"] = [_p, _int, _i64, _i64, _i64, _p, C.POINTER(GramJob), _int, _p, _p, _int, _p]
+
 _lib = None
 
 

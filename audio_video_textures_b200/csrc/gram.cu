@@ -50,14 +50,29 @@ constexpr uint32_t make_idesc(int m, bool is_signed) {
            (uint32_t(m >> 4) << 24);
 }
 
-struct GramArgs {
-    int64_t n, kp, row0, rows, ldd;
-    const int64_t *sqnorm;
+// One rectangle of the distance matrix: A rows [row0, row0+rows) x output columns [col0, col0+cols).
+//   D  (nullable): direct destination,      D [(r - d_row0)  * ldd + c]
+//   DT (nullable): transposed destination,  DT[(c - dt_row0) * ldt + r]   -- may be PEER memory (NVLink)
+//   symmetric: rows == cols range; only tiles touching the upper triangle are computed, the direct store
+//   takes r <= c and the transposed store r < c (the mirror image).
+struct GramJob {
+    int64_t row0, rows, col0, cols;
     float *D;
+    int64_t d_row0, ldd;
+    float *DT;
+    int64_t dt_row0, ldt;
+    int symmetric, count_stats, TM, TN, tile_begin, pad_;
+};
+constexpr int MAX_JOBS = 16;
+
+struct GramArgs {
+    int64_t n, kp;
+    const int64_t *sqnorm;
     double *sum;
     unsigned long long *nnz;
-    int symmetric, TM, TN, num_tiles;
     uint32_t idesc;                     // kind::i8 instruction descriptor (signed or unsigned operands)
+    int num_jobs, num_tiles;
+    GramJob jobs[MAX_JOBS];
 };
 
 // ------------------------------------------------------------------ PTX wrappers
@@ -160,14 +175,15 @@ struct EpiStats {
 // reuse the accumulator while the stores drain.
 
 template <typename Release>
-__device__ __forceinline__ void epilogue_tile(const GramArgs &args, uint32_t t_base, int64_t r0, int64_t c0,
-                                              int lane, float *tile, Release release, EpiStats &st) {
-    const int64_t row_end = args.row0 + args.rows;
+__device__ __forceinline__ void epilogue_tile(const GramArgs &args, const GramJob &job, uint32_t t_base, int64_t r0,
+                                              int64_t c0, int lane, float *tile, Release release, EpiStats &st) {
+    const int64_t row_end = job.row0 + job.rows, col_end = job.col0 + job.cols;
     const int64_t r = r0 + lane;
     const bool r_ok = r < row_end;
     const uint32_t nr = r_ok ? (uint32_t)__ldg(args.sqnorm + r) : 0u;
     int64_t rows_here = row_end - r0;                              // valid rows of this warp's 32
     if (rows_here > 32) rows_here = 32;
+    const bool sym = job.symmetric != 0;
 #pragma unroll 1
     for (int cc = 0; cc < BN / 32; ++cc) {
         uint32_t g[32];
@@ -178,14 +194,15 @@ __device__ __forceinline__ void epilogue_tile(const GramArgs &args, uint32_t t_b
             if (lane == 0) release();
         }
         const int64_t cbase = c0 + cc * 32;
-        if (cbase >= args.n || rows_here <= 0) continue;
-        if (args.symmetric && cbase + 31 < r0) continue;          // whole chunk below the diagonal for this warp
-        const uint32_t nc_lane = (cbase + lane < args.n) ? (uint32_t)__ldg(args.sqnorm + cbase + lane) : 0u;
+        if (cbase >= col_end || rows_here <= 0) continue;
+        if (sym && cbase + 31 < r0) continue;                     // whole chunk below the diagonal for this warp
+        const uint32_t nc_lane = (cbase + lane < col_end) ? (uint32_t)__ldg(args.sqnorm + cbase + lane) : 0u;
         __syncwarp();                                             // previous chunk's tile reads are finished
         // sigma statistics: fp32 / int partials per 32-element chunk, promoted to fp64 once per chunk
         // (a per-element DFMA chain made the epilogue, not the MMAs, the critical path at K = 12288)
         float cs = 0.f;
         int cz = 0;
+        float *dt = (job.DT != nullptr) ? job.DT + (cbase - job.dt_row0) * job.ldt + r : nullptr;
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
             const uint32_t nc = __shfl_sync(0xffffffffu, nc_lane, j);
@@ -193,36 +210,40 @@ __device__ __forceinline__ void epilogue_tile(const GramArgs &args, uint32_t t_b
             const float d = __fsqrt_rn(__uint2float_rn(d2));
             tile[lane * EPI_PITCH + j] = d;
             const int64_t c = cbase + j;
-            if (args.symmetric && r_ok && c < args.n && r < c) {
-                args.D[c * args.ldd + r] = d;                     // mirrored store: coalesced across the warp
+            if (dt != nullptr && r_ok && c < col_end && (!sym || r < c)) {
+                dt[j * job.ldt] = d;                              // transposed store: coalesced across the warp
                 cs += d;
                 cz += (d != 0.f);
             }
         }
         __syncwarp();
-        const int64_t c = cbase + lane;                           // this lane's column for the row stores
-        const bool c_ok = c < args.n;
-        float *dst = args.D + (r0 - args.row0) * args.ldd + c;
-        if (!args.symmetric) {
+        if (job.D != nullptr) {
+            const int64_t c = cbase + lane;                       // this lane's column for the row stores
+            const bool c_ok = c < col_end;
+            float *dst = job.D + (r0 - job.d_row0) * job.ldd + c;
 #pragma unroll 8
             for (int i = 0; i < 32; ++i) {
-                if (i < rows_here && c_ok) {
+                if (i < rows_here && c_ok && (!sym || r0 + i <= c)) {
                     const float d = tile[i * EPI_PITCH + lane];
-                    dst[i * args.ldd] = d;
+                    dst[i * job.ldd] = d;
                     cs += d;
                     cz += (d != 0.f);
                 }
             }
+        }
+        if (job.count_stats) {
             st.s += (double)cs;
             st.z += (unsigned long long)cz;
-        } else {
-#pragma unroll 8
-            for (int i = 0; i < 32; ++i)
-                if (i < rows_here && c_ok && r0 + i <= c) dst[i * args.ldd] = tile[i * EPI_PITCH + lane];
-            st.s += 2.0 * (double)cs;                             // each off-diagonal distance appears twice
-            st.z += 2ull * (unsigned long long)cz;
         }
     }
+}
+
+// tile index over all jobs -> (job, local tile index)
+__device__ __forceinline__ int find_job(const GramArgs &args, int t, int *local) {
+    int j = 0;
+    while (j + 1 < args.num_jobs && t >= args.jobs[j + 1].tile_begin) ++j;
+    *local = t - args.jobs[j].tile_begin;
+    return j;
 }
 
 __device__ __forceinline__ void epilogue_flush(const GramArgs &args, EpiStats &st, int lane) {
@@ -324,9 +345,10 @@ gram_l2_s8_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             int stage = 0;
             uint32_t phase = 0;
             for (int t = blockIdx.x; t < args.num_tiles; t += gridDim.x) {
-                int tm, tn;
-                decode_tile(t, args.TM, args.TN, args.symmetric, &tm, &tn);
-                const int row_a = int(args.row0) + tm * BM, row_b = tn * BN;
+                int tm, tn, lt;
+                const GramJob &job = args.jobs[find_job(args, t, &lt)];
+                decode_tile(lt, job.TM, job.TN, job.symmetric, &tm, &tn);
+                const int row_a = int(job.row0) + tm * BM, row_b = int(job.col0) + tn * BN;
                 for (int kb = 0; kb < KB; ++kb) {
                     mbar_wait(empty_bar + 8 * stage, phase ^ 1);
                     const uint32_t sa = tiles + stage * STAGE_BYTES, sb = sa + A_BYTES;
@@ -370,14 +392,15 @@ gram_l2_s8_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         uint32_t acc_phase = 0;
         EpiStats st{0.0, 0ull};
         for (int t = blockIdx.x; t < args.num_tiles; t += gridDim.x) {
-            int tm, tn;
-            decode_tile(t, args.TM, args.TN, args.symmetric, &tm, &tn);
+            int tm, tn, lt;
+            const GramJob &job = args.jobs[find_job(args, t, &lt)];
+            decode_tile(lt, job.TM, job.TN, job.symmetric, &tm, &tn);
             mbar_wait(tfull_bar + 8 * acc, acc_phase);
             tc_fence_after();
             const uint32_t t_base = tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(acc * BN);
             const uint32_t release = tempty_bar + 8 * acc;
-            epilogue_tile(args, t_base, args.row0 + int64_t(tm) * BM + quarter * 32, int64_t(tn) * BN, lane,
-                          epi_tile, [release]() { mbar_arrive(release); }, st);
+            epilogue_tile(args, job, t_base, job.row0 + int64_t(tm) * BM + quarter * 32, job.col0 + int64_t(tn) * BN,
+                          lane, epi_tile, [release]() { mbar_arrive(release); }, st);
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
         epilogue_flush(args, st, lane);
@@ -531,10 +554,11 @@ gram_l2_s8_2cta_kernel(const __grid_constant__ CUtensorMap map, const GramArgs a
             int stage = 0;
             uint32_t phase = 0;
             for (int t = cluster_id; t < args.num_tiles; t += num_clusters) {
-                int tm, tn;
-                decode_tile2(t, args.TM, args.TN, args.symmetric, &tm, &tn);
-                int row_a = int(args.row0) + tm * BM2 + int(rank) * BM;
-                int row_b = tn * BN + int(rank) * (BN / 2);
+                int tm, tn, lt;
+                const GramJob &job = args.jobs[find_job(args, t, &lt)];
+                decode_tile2(lt, job.TM, job.TN, job.symmetric, &tm, &tn);
+                int row_a = int(job.row0) + tm * BM2 + int(rank) * BM;
+                int row_b = int(job.col0) + tn * BN + int(rank) * (BN / 2);
                 if (row_a >= args.n) row_a = 0;           // fully out-of-range half: load anything, stores are masked
                 if (row_b >= args.n) row_b = 0;
                 for (int kb = 0; kb < KB; ++kb) {
@@ -581,14 +605,16 @@ gram_l2_s8_2cta_kernel(const __grid_constant__ CUtensorMap map, const GramArgs a
         uint32_t acc_phase = 0;
         EpiStats st{0.0, 0ull};
         for (int t = cluster_id; t < args.num_tiles; t += num_clusters) {
-            int tm, tn;
-            decode_tile2(t, args.TM, args.TN, args.symmetric, &tm, &tn);
+            int tm, tn, lt;
+            const GramJob &job = args.jobs[find_job(args, t, &lt)];
+            decode_tile2(lt, job.TM, job.TN, job.symmetric, &tm, &tn);
             mbar_wait(tfull_bar + 8 * acc, acc_phase);
             tc_fence_after();
             const uint32_t t_base = tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(acc * BN);
             const uint32_t release = tempty_bar + 8 * acc;
-            epilogue_tile(args, t_base, args.row0 + int64_t(tm) * BM2 + int64_t(rank) * BM + quarter * 32,
-                          int64_t(tn) * BN, lane, epi_tile, [release]() { mbar_arrive_cluster(release, 0); }, st);
+            epilogue_tile(args, job, t_base, job.row0 + int64_t(tm) * BM2 + int64_t(rank) * BM + quarter * 32,
+                          job.col0 + int64_t(tn) * BN, lane, epi_tile,
+                          [release]() { mbar_arrive_cluster(release, 0); }, st);
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
         epilogue_flush(args, st, lane);
@@ -631,37 +657,60 @@ int make_map(EncodeTiledFn enc, CUtensorMap *map, const void *base, int64_t n, i
     return 0;
 }
 
-int launch_gram(const void *operand, bool is_signed, int64_t n, int64_t k_extent, int64_t pitch, const int64_t *sqnorm,
-                int64_t row0, int64_t rows, int symmetric, float *D, int64_t ldd, double *sum, unsigned long long *nnz,
-                int device, void *stream) {
+int launch_gram_jobs(const void *operand, bool is_signed, int64_t n, int64_t k_extent, int64_t pitch,
+                     const int64_t *sqnorm, const AvtexGramJob *jobs, int num_jobs, double *sum,
+                     unsigned long long *nnz, int device, void *stream) {
     AVTEX_ENTER(device);
     AVTEX_REQUIRE(n >= 1 && n < (int64_t(1) << 30) && k_extent >= 1 && k_extent < (int64_t(1) << 31),
                   "gram_l2: bad shape n=%lld k=%lld", (long long)n, (long long)k_extent);
     AVTEX_REQUIRE(pitch >= k_extent && pitch % 16 == 0 && (reinterpret_cast<uintptr_t>(operand) & 15) == 0,
                   "gram_l2: operand rows must be 16-byte aligned (pitch %lld)", (long long)pitch);
-    AVTEX_REQUIRE(rows >= 1 && row0 >= 0 && row0 + rows <= n && ldd >= n, "gram_l2: bad row block [%lld,+%lld)",
-                  (long long)row0, (long long)rows);
-    AVTEX_REQUIRE(!symmetric || (row0 == 0 && rows == n), "gram_l2: symmetric mode needs the full matrix");
+    AVTEX_REQUIRE(num_jobs >= 1 && num_jobs <= MAX_JOBS, "gram_l2: 1..%d jobs per launch (got %d)", MAX_JOBS, num_jobs);
     AVTEX_REQUIRE((sum == nullptr) == (nnz == nullptr), "gram_l2: sum and nnz go together");
     int cc = 0, sms = 0;
     if (int rc = avtex_device_info(device, &sms, &cc)) return rc;
     AVTEX_REQUIRE(cc == 100, "gram_l2: needs an sm_100 device (tcgen05 kind::i8), got cc %d", cc);
+    const char *mode = getenv("AVTEX_GRAM_MODE");                  // "1cta" selects the single-CTA kernel
+    const bool two_cta = !(mode != nullptr && mode[0] == '1');
+    const int bm = two_cta ? BM2 : BM;
+
+    GramArgs a;
+    a.n = n; a.kp = k_extent; a.sqnorm = sqnorm; a.sum = sum; a.nnz = nnz;
+    a.idesc = make_idesc(bm, is_signed);
+    a.num_jobs = num_jobs;
+    int total = 0;
+    for (int j = 0; j < num_jobs; ++j) {
+        const AvtexGramJob &in = jobs[j];
+        AVTEX_REQUIRE(in.rows >= 1 && in.cols >= 1 && in.row0 >= 0 && in.col0 >= 0 && in.row0 + in.rows <= n &&
+                          in.col0 + in.cols <= n,
+                      "gram_l2: job %d rectangle [%lld,+%lld) x [%lld,+%lld) outside the %lld frames", j,
+                      (long long)in.row0, (long long)in.rows, (long long)in.col0, (long long)in.cols, (long long)n);
+        AVTEX_REQUIRE(!in.symmetric || (in.row0 == in.col0 && in.rows == in.cols),
+                      "gram_l2: job %d is symmetric but its row and column ranges differ", j);
+        AVTEX_REQUIRE(in.D != nullptr || in.DT != nullptr, "gram_l2: job %d has no destination", j);
+        AVTEX_REQUIRE(in.D == nullptr || (in.ldd >= in.col0 + in.cols && in.d_row0 <= in.row0),
+                      "gram_l2: job %d direct destination too small", j);
+        AVTEX_REQUIRE(in.DT == nullptr || (in.ldt >= in.row0 + in.rows && in.dt_row0 <= in.col0),
+                      "gram_l2: job %d transposed destination too small", j);
+        GramJob &o = a.jobs[j];
+        o.row0 = in.row0; o.rows = in.rows; o.col0 = in.col0; o.cols = in.cols;
+        o.D = in.D; o.d_row0 = in.d_row0; o.ldd = in.ldd;
+        o.DT = in.DT; o.dt_row0 = in.dt_row0; o.ldt = in.ldt;
+        o.symmetric = in.symmetric ? 1 : 0;
+        o.count_stats = (in.count_stats && sum != nullptr) ? 1 : 0;
+        o.TM = int((in.rows + bm - 1) / bm);
+        o.TN = int((in.cols + BN - 1) / BN);
+        o.tile_begin = total;
+        o.pad_ = 0;
+        total += two_cta ? count_tiles2(o.TM, o.TN, o.symmetric) : count_tiles(o.TM, o.TN, o.symmetric);
+    }
+    a.num_tiles = total;
 
     EncodeTiledFn enc;
     if (int rc = get_encode_fn(&enc)) return rc;
-    GramArgs a;
-    a.n = n; a.kp = k_extent; a.row0 = row0; a.rows = rows; a.ldd = ldd;
-    a.sqnorm = sqnorm; a.D = D; a.sum = sum; a.nnz = nnz;
-    a.symmetric = symmetric ? 1 : 0;
-    const char *mode = getenv("AVTEX_GRAM_MODE");                  // "1cta" selects the single-CTA kernel
-    const bool two_cta = !(mode != nullptr && mode[0] == '1');
     if (two_cta) {
         CUtensorMap map;
         if (int rc = make_map(enc, &map, operand, n, k_extent, pitch, BM)) return rc;
-        a.TM = int((rows + BM2 - 1) / BM2);
-        a.TN = int((n + BN - 1) / BN);
-        a.num_tiles = count_tiles2(a.TM, a.TN, a.symmetric);
-        a.idesc = make_idesc(BM2, is_signed);
         static bool attr2_set[64] = {false};
         if (device < 64 && !attr2_set[device]) {
             AVTEX_CUDA(cudaFuncSetAttribute(gram_l2_s8_2cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES));
@@ -676,10 +725,6 @@ int launch_gram(const void *operand, bool is_signed, int64_t n, int64_t k_extent
     CUtensorMap map_a, map_b;
     if (int rc = make_map(enc, &map_a, operand, n, k_extent, pitch, BM)) return rc;
     if (int rc = make_map(enc, &map_b, operand, n, k_extent, pitch, BN)) return rc;
-    a.TM = int((rows + BM - 1) / BM);
-    a.TN = int((n + BN - 1) / BN);
-    a.num_tiles = count_tiles(a.TM, a.TN, a.symmetric);
-    a.idesc = make_idesc(BM, is_signed);
     static bool attr_set[64] = {false};
     if (device < 64 && !attr_set[device]) {
         AVTEX_CUDA(cudaFuncSetAttribute(gram_l2_s8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
@@ -689,6 +734,22 @@ int launch_gram(const void *operand, bool is_signed, int64_t n, int64_t k_extent
     gram_l2_s8_kernel<<<grid, NUM_THREADS, SMEM_BYTES, as_stream(stream)>>>(map_a, map_b, a);
     AVTEX_LAUNCH_CHECK();
     return 0;
+}
+
+// The two classic shapes as one job: the full symmetric matrix, or a row block against all columns.
+int launch_gram(const void *operand, bool is_signed, int64_t n, int64_t k_extent, int64_t pitch, const int64_t *sqnorm,
+                int64_t row0, int64_t rows, int symmetric, float *D, int64_t ldd, double *sum, unsigned long long *nnz,
+                int device, void *stream) {
+    AVTEX_REQUIRE(rows >= 1 && row0 >= 0 && row0 + rows <= n && ldd >= n, "gram_l2: bad row block [%lld,+%lld)",
+                  (long long)row0, (long long)rows);
+    AVTEX_REQUIRE(!symmetric || (row0 == 0 && rows == n), "gram_l2: symmetric mode needs the full matrix");
+    AvtexGramJob job;
+    job.row0 = row0; job.rows = rows; job.col0 = 0; job.cols = n;
+    job.D = D; job.d_row0 = row0; job.ldd = ldd;
+    job.DT = symmetric ? D : nullptr; job.dt_row0 = 0; job.ldt = ldd;
+    job.symmetric = symmetric ? 1 : 0;
+    job.count_stats = 1;
+    return launch_gram_jobs(operand, is_signed, n, k_extent, pitch, sqnorm, &job, 1, sum, nnz, device, stream);
 }
 
 }  // namespace
@@ -703,6 +764,12 @@ extern "C" int avtex_gram_l2_u8(const uint8_t *frames, int64_t n, int64_t k, int
                                 int64_t row0, int64_t rows, int symmetric, float *D, int64_t ldd,
                                 double *sum, unsigned long long *nnz, int device, void *stream) {
     return launch_gram(frames, false, n, k, ld, sqnorm, row0, rows, symmetric, D, ldd, sum, nnz, device, stream);
+}
+
+extern "C" int avtex_gram_l2_jobs(const void *operand, int operand_signed, int64_t n, int64_t k, int64_t ld,
+                                  const int64_t *sqnorm, const AvtexGramJob *h_jobs, int num_jobs, double *sum,
+                                  unsigned long long *nnz, int device, void *stream) {
+    return launch_gram_jobs(operand, operand_signed != 0, n, k, ld, sqnorm, h_jobs, num_jobs, sum, nnz, device, stream);
 }
 
 extern "C" int avtex_gram_tile_schedule2(int TM, int TN, int symmetric, int *tm_out, int *tn_out, int capacity) {

@@ -43,7 +43,8 @@ def plan_shards(n: int, filter_size: int, stride: int, world: int, rank: int) ->
     if a0 >= m:
         raise ValueError(f"rank {rank} of {world} would own no rows of the {m} x {m} matrix")
     a1h = min(m, a1 + 1)
-    return ShardPlan(n, m, world, rank, shard, a0, a1, a1h, a0 * stride, (a1h - 1) * stride + filter_size)
+    r_hi = n if a1 == m else (a1h - 1) * stride + filter_size      # the last rank keeps the unused tail rows too
+    return ShardPlan(n, m, world, rank, shard, a0, a1, a1h, a0 * stride, r_hi)
 
 
 def make_exchange(plan: ShardPlan, group=None):
@@ -79,6 +80,81 @@ def allreduce_stats(stats: torch.Tensor, group=None) -> torch.Tensor:
     return out
 
 
+def pair_split(lo: int, hi: int) -> int:
+    """Column split point of core_j for the pair (i < j): rank i computes core_i x [lo, mid) and rank j
+    computes [mid, hi) x core_i, each pushing the transpose to the other, so both do half of the rectangle
+    whatever the number of ranks.  Aligned to the 256-wide tile."""
+    mid = lo + (hi - lo) // 2
+    mid = lo + (mid - lo + 255) // 256 * 256
+    return min(mid, hi)
+
+
+class SymmetricShardWorkspace:
+    """D1 row shards in torch symmetric memory (peer-mapped over NVLink / NVSwitch).
+
+    Row sharding alone forfeits the factor-2 symmetry of the distance matrix: rank I needs D1[rows_I, :],
+    and D1[rows_I, cols_J] is the transpose of D1[rows_J, cols_I] that rank J needs.  Here each off-diagonal
+    rectangle is split between the two ranks; the same tcgen05 kernel that computes a tile stores it
+    locally and pushes the transposed tile straight into the peer's shard (coalesced 128-byte NVLink
+    stores from the epilogue), so every rank does N^2/(2G) pairs and no separate exchange step exists.
+    """
+
+    def __init__(self, n: int, filter_size: int, stride: int, rank: int, world: int, device, group=None):
+        import torch.distributed._symmetric_memory as symm_mem
+        self.n, self.fs, self.stride, self.rank, self.world = n, filter_size, stride, rank, world
+        self.plans = [plan_shards(n, filter_size, stride, world, r) for r in range(world)]
+        self.plan = self.plans[rank]
+        self.ld = (n + 31) // 32 * 32
+        rows_max = max(p.r_hi - p.r_lo for p in self.plans)
+        group = dist.group.WORLD if group is None else group
+        self.buf = symm_mem.empty((rows_max, self.ld), dtype=torch.float32, device=device)
+        self.hdl = symm_mem.rendezvous(self.buf, group.group_name)
+        self.ptrs = [int(p) for p in self.hdl.buffer_ptrs]
+        self.group = group
+
+    def core(self, r: int):
+        """Disjoint cover of the frame rows: the rows whose distances rank r is responsible for."""
+        p = self.plans[r]
+        return p.a0 * self.stride, (self.n if r == self.world - 1 else p.a1 * self.stride)
+
+    def D1(self) -> torch.Tensor:
+        p = self.plan
+        return self.buf[:p.r_hi - p.r_lo, :self.n]
+
+    def jobs(self):
+        me, p = self.rank, self.plan
+        lo, hi = self.core(me)
+        mine = dict(D=self.ptrs[me], d_row0=p.r_lo, ldd=self.ld)
+        out = [dict(row0=lo, rows=hi - lo, col0=lo, cols=hi - lo, symmetric=1, count_stats=1,
+                    DT=self.ptrs[me], dt_row0=p.r_lo, ldt=self.ld, **mine)]
+        for other in range(self.world):
+            if other == me:
+                continue
+            olo, ohi = self.core(other)
+            peer = dict(DT=self.ptrs[other], dt_row0=self.plans[other].r_lo, ldt=self.ld)
+            if me < other:                                  # my rows x the first half of the peer's columns
+                mid = pair_split(olo, ohi)
+                if mid > olo:
+                    out.append(dict(row0=lo, rows=hi - lo, col0=olo, cols=mid - olo, symmetric=0, count_stats=1,
+                                    **peer, **mine))
+            else:                                           # the second half of my rows x the peer's columns
+                mid = pair_split(lo, hi)
+                if hi > mid:
+                    out.append(dict(row0=mid, rows=hi - mid, col0=olo, cols=ohi - olo, symmetric=0, count_stats=1,
+                                    **peer, **mine))
+        if p.r_hi > hi:                                     # halo rows (the next rank's first rows): local, all columns
+            out.append(dict(row0=hi, rows=p.r_hi - hi, col0=0, cols=self.n, symmetric=0, count_stats=0, **mine))
+        return out
+
+    def gram(self, pf: engine.PackedFrames, stats=None) -> torch.Tensor:
+        """Fills this rank's D1 shard (its own tiles + the tiles peers push).  Stream-ordered barriers on
+        both sides: peers must be done reading the previous contents, and done pushing, respectively."""
+        self.hdl.barrier(channel=0)
+        engine.gram_l2_jobs(pf, self.jobs(), stats)
+        self.hdl.barrier(channel=1)
+        return self.D1()
+
+
 @dataclass
 class ShardResult:
     plan: ShardPlan
@@ -97,15 +173,21 @@ class ShardResult:
 
 def classic_sharded(frames: torch.Tensor, filter_size: int, stride: int, rank: int, world: int,
                     p: float = 0.7, alpha: float = 0.997, sigma_factor=None, threshold=None, group=None,
-                    packed: engine.PackedFrames | None = None) -> ShardResult:
+                    packed: engine.PackedFrames | None = None,
+                    workspace: SymmetricShardWorkspace | None = None) -> ShardResult:
     """Distance + filter + converged future cost (+ sigma3 / P3 / P3_new when sigma_factor is given) for
-    this rank's rows.  `frames`: the full [N, ...] uint8 clip on this rank's device."""
+    this rank's rows.  `frames`: the full [N, ...] uint8 clip on this rank's device.  With a
+    SymmetricShardWorkspace the distance stage uses the symmetry across ranks (peer pushes over NVLink);
+    without one every rank computes its full row block locally."""
     n = frames.shape[0]
     plan = plan_shards(n, filter_size, stride, world, rank)
     pf = engine.pack_frames(frames) if packed is None else packed
     if not pf.exact_ok:
         raise engine._lib.AvtexError(f"sharded path needs byte frames inside the Gram domain: {pf.reason}")
-    D1 = engine.gram_l2(pf, plan.r_lo, plan.r_hi - plan.r_lo, symmetric=False)
+    if workspace is not None and world > 1:
+        D1 = workspace.gram(pf)                            # symmetric across ranks: transposed tiles pushed to peers
+    else:
+        D1 = engine.gram_l2(pf, plan.r_lo, plan.r_hi - plan.r_lo, symmetric=False)
     D2, D3 = engine.diag_filter(D1, filter_size, stride, p=p, m=plan.m, a0=plan.a0,
                                 rows_out=plan.a1h - plan.a0, in_row0=plan.r_lo)
     own = plan.a1 - plan.a0

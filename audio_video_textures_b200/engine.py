@@ -165,6 +165,22 @@ def gram_l2(pf: PackedFrames, row0: int = 0, rows: int | None = None, symmetric:
     return D
 
 
+def gram_l2_jobs(pf: PackedFrames, jobs: list, stats: torch.Tensor | None = None, device=None):
+    """K1, general form: `jobs` is a list of dicts with the fields of AvtexGramJob (D / DT are raw device
+    pointers, possibly into a peer GPU's symmetric-memory buffer)."""
+    arr = (_lib.GramJob * len(jobs))()
+    for dst, j in zip(arr, jobs):
+        dst.row0, dst.rows, dst.col0, dst.cols = j["row0"], j["rows"], j["col0"], j["cols"]
+        dst.D, dst.d_row0, dst.ldd = j.get("D"), j.get("d_row0", 0), j.get("ldd", 0)
+        dst.DT, dst.dt_row0, dst.ldt = j.get("DT"), j.get("dt_row0", 0), j.get("ldt", 0)
+        dst.symmetric, dst.count_stats = int(j.get("symmetric", 0)), int(j.get("count_stats", 0))
+    n = pf.packed.shape[0]
+    s, z = _stats_ptrs(stats)
+    k_extent = pf.packed.shape[1] if pf.signed else pf.k
+    _lib.call("avtex_gram_l2_jobs", _lib.ptr(pf.packed), 1 if pf.signed else 0, n, k_extent, pf.packed.stride(0),
+              _lib.ptr(pf.sqnorm), arr, len(jobs), s, z, _dev(pf.packed), _stream(pf.packed))
+
+
 def pairdist_direct(frames: torch.Tensor, row0: int = 0, rows: int | None = None,
                     stats: torch.Tensor | None = None) -> torch.Tensor:
     """K1 fallback: direct difference in fp32 (any float features, or uint8)."""

@@ -172,6 +172,9 @@ def run_ours(args):
     peaks = load_peaks()
     gram_ms, step_ms = [], []
     state = {}
+    workspace = None
+    if world > 1 and not args.no_symmetric:
+        workspace = avdist.SymmetricShardWorkspace(n, fs, stride, rank, world, dev)
 
     def one_step(timed: bool):
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
@@ -191,7 +194,7 @@ def run_ours(args):
             state.update(D1=D1, D3n=D3n, sweeps=fc.n_sweeps, m=D3.shape[0], rows=n)
         else:
             ev[1].record()
-            res = avdist.classic_sharded(frames, fs, stride, rank, world, packed=pf)
+            res = avdist.classic_sharded(frames, fs, stride, rank, world, packed=pf, workspace=workspace)
             ev[2].record()       # (gram is the first kernel after ev[1]; the sharded call is timed as a whole)
             launches = res.launches
             state.update(D3n=res.D3_new, sweeps=res.n_sweeps, m=res.plan.m, rows=res.plan.r_hi - res.plan.r_lo)
@@ -270,7 +273,8 @@ def run_ours(args):
                                f"{wl['h']}x{wl['w']} RGB (K={k}) -> M={m}, {state['sweeps']} future-cost sweeps",
                    "name": args.workload, "l2": "256 MB L2 flush between timed steps",
                    "sharding": "single GPU" if world == 1 else
-                   (f"rows over {world} ranks, N=5000*sqrt(G)" if args.workload == "c2" else f"rows over {world} ranks")},
+                   (f"rows over {world} ranks, N=5000*sqrt(G)" if args.workload == "c2" else f"rows over {world} ranks") +
+                   ("" if world == 1 or args.no_symmetric else "; symmetric Gram, transposed tiles pushed to peer shards over NVLink")},
         "gpu_launches": launches, "wall_s": wall,
     }
     if world == 1:
@@ -325,6 +329,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--no_symmetric", action="store_true",
+                    help="N>1: plain row shards (every rank computes its full row block) instead of peer pushes")
     ap.add_argument("--cpu_budget", type=float, default=20.0, help="seconds of CPU work for the baseline sample")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -83,6 +83,29 @@ AVTEX_API int avtex_gram_l2_s8(const int8_t *packed, int64_t n, int64_t kp, cons
 AVTEX_API int avtex_gram_l2_u8(const uint8_t *frames, int64_t n, int64_t k, int64_t ld, const int64_t *sqnorm,
                      int64_t row0, int64_t rows, int symmetric, float *D, int64_t ldd,
                      double *sum, unsigned long long *nnz, int device, void *stream);
+/* General form (one launch, up to 16 rectangles): job j covers frames rows [row0, row0+rows) against
+ * output columns [col0, col0+cols) and writes
+ *     D [(r - d_row0)  * ldd + c] = d(r, c)      if D  != NULL   (direct)
+ *     DT[(c - dt_row0) * ldt + r] = d(r, c)      if DT != NULL   (transposed)
+ * `symmetric` jobs (row range == column range) compute only tiles touching the upper triangle and store
+ * r <= c directly and r < c transposed.  DT may point into ANOTHER GPU's memory (peer-mapped, e.g. a
+ * torch symmetric-memory buffer): the transposed tile is then pushed over NVLink by the same kernel that
+ * computes it, which is how the row-sharded multi-GPU path keeps the factor-2 symmetry saving without a
+ * separate exchange step (dist.py).  count_stats: add this job's stored elements to sum / nnz.
+ * h_jobs is a HOST array, copied into the launch parameters.
+ * operand: int8 centred frames (operand_signed = 1) or raw uint8 frames (0); ld = row pitch in bytes. */
+typedef struct AvtexGramJob {
+    int64_t row0, rows, col0, cols;
+    float *D;
+    int64_t d_row0, ldd;
+    float *DT;
+    int64_t dt_row0, ldt;
+    int symmetric, count_stats;
+} AvtexGramJob;
+AVTEX_API int avtex_gram_l2_jobs(const void *operand, int operand_signed, int64_t n, int64_t k, int64_t ld,
+                       const int64_t *sqnorm, const AvtexGramJob *h_jobs, int num_jobs, double *sum,
+                       unsigned long long *nnz, int device, void *stream);
+
 /* sqnorm[i] = sum_c frames[i,c]^2 (exact); max_centred (nullable, zeroed by the caller) receives
  * max_i sum_c (frames[i,c]-128)^2 via atomicMax.  HBM-bound: one read of the frames. */
 AVTEX_API int avtex_frame_norms_u8(const uint8_t *frames, int64_t n, int64_t k, int64_t ld, int64_t *sqnorm,

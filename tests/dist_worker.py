@@ -20,7 +20,9 @@ def main():
     n, h, w, fs, stride = (int(v) for v in sys.argv[1:6])
     th, f = 0.08, 4.5
     frames = synth_video(n, h, w, seed=2).cuda()
-    res = avd.classic_sharded(frames, fs, stride, rank, world, sigma_factor=f, threshold=th)
+    mode = sys.argv[6] if len(sys.argv) > 6 else "rows"
+    ws = avd.SymmetricShardWorkspace(n, fs, stride, rank, world, frames.device) if mode == "sym" else None
+    res = avd.classic_sharded(frames, fs, stride, rank, world, sigma_factor=f, threshold=th, workspace=ws)
     rowptr, colidx = avd.gather_survivors(res)
     # single-GPU result on every rank
     pf = engine.pack_frames(frames)
@@ -48,7 +50,7 @@ def main():
     flag = torch.tensor([int(all(ok.values()))], device="cuda")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:
-        print("DIST_CHECK", "PASS" if int(flag) == 1 else "FAIL", ok, "world", world, "M", p.m, "sweeps", res.n_sweeps)
+        print("DIST_CHECK", "PASS" if int(flag) == 1 else "FAIL", mode, ok, "world", world, "M", p.m, "sweeps", res.n_sweeps)
     else:
         if not all(ok.values()):
             print("rank", rank, ok)

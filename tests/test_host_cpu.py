@@ -129,10 +129,54 @@ def test_shard_plan_covers_rows_and_halos(n, fs, stride, world):
         p = avd.plan_shards(n, fs, stride, world, r)
         assert p.m == m and p.a0 == r * p.shard and p.a0 < p.a1 <= m
         assert p.a1h == min(m, p.a1 + 1)                              # one halo row for the P shift
-        assert p.r_lo == p.a0 * stride and p.r_hi == (p.a1h - 1) * stride + fs <= n
+        assert p.r_lo == p.a0 * stride and p.r_hi <= n
+        assert p.r_hi == (n if p.a1 == m else (p.a1h - 1) * stride + fs)
         assert p.padded >= m and p.padded % world == 0
         owned.extend(range(p.a0, p.a1))
     assert owned == list(range(m))
+
+
+@pytest.mark.parametrize("n,fs,stride,world", [(7072, 40, 4, 2), (12000, 40, 4, 8), (2051, 40, 4, 3), (333, 16, 1, 2)])
+def test_symmetric_shard_jobs_cover_every_needed_element_once(n, fs, stride, world):
+    """Host logic of the peer-push scheme (no GPU, no process group): over all ranks, the direct and the
+    transposed destinations of the job lists cover every (row, col) of every rank's D1 shard exactly once."""
+    from audio_video_textures_b200 import dist as avd
+
+    class _WS(avd.SymmetricShardWorkspace):
+        def __init__(self, rank):                           # geometry only: no symmetric-memory allocation
+            self.n, self.fs, self.stride, self.rank, self.world = n, fs, stride, rank, world
+            self.plans = [avd.plan_shards(n, fs, stride, world, r) for r in range(world)]
+            self.plan = self.plans[rank]
+            self.ld = (n + 31) // 32 * 32
+            self.ptrs = [1000 + r for r in range(world)]     # stand-in "pointers" = rank ids
+
+    plans = [avd.plan_shards(n, fs, stride, world, r) for r in range(world)]
+    cover = [np.zeros((p.r_hi - p.r_lo, n), dtype=np.int16) for p in plans]
+    work = []
+    for r in range(world):
+        jobs = _WS(r).jobs()
+        assert len(jobs) <= 16
+        pairs = 0
+        for j in jobs:
+            rs, cs = slice(j["row0"], j["row0"] + j["rows"]), slice(j["col0"], j["col0"] + j["cols"])
+            tri = None
+            if j["symmetric"]:
+                assert j["row0"] == j["col0"] and j["rows"] == j["cols"]
+                tri = np.triu(np.ones((j["rows"], j["cols"]), dtype=np.int16))
+            if j.get("D") is not None:
+                owner = j["D"] - 1000
+                assert owner == r
+                blk = cover[owner][rs.start - j["d_row0"]: rs.stop - j["d_row0"], cs]
+                blk += 1 if tri is None else tri
+            if j.get("DT") is not None:
+                owner = j["DT"] - 1000
+                blk = cover[owner][cs.start - j["dt_row0"]: cs.stop - j["dt_row0"], rs]
+                blk += 1 if tri is None else (np.triu(np.ones((j["rows"], j["cols"]), dtype=np.int16), 1)).T
+            pairs += j["rows"] * j["cols"] // (2 if j["symmetric"] else 1)
+        work.append(pairs)
+    for c in cover:
+        assert c.min() == 1 and c.max() == 1
+    assert max(work) <= 1.25 * (n * n / (2 * world)) + 300 * n           # balanced up to halos and tile rounding
 
 
 def _free_port():
