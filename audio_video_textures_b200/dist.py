@@ -142,9 +142,11 @@ class SymmetricShardWorkspace:
                 if hi > mid:
                     out.append(dict(row0=mid, rows=hi - mid, col0=olo, cols=ohi - olo, symmetric=0, count_stats=1,
                                     **peer, **mine))
-        if p.r_hi > hi:                                     # halo rows (the next rank's first rows): local, all columns
-            out.append(dict(row0=hi, rows=p.r_hi - hi, col0=0, cols=self.n, symmetric=0, count_stats=0, **mine))
         return out
+
+    def halo_rows(self) -> int:
+        """Rows past this rank's core that its filter outputs read: the next rank's first rows."""
+        return self.plan.r_hi - self.core(self.rank)[1]
 
     def gram(self, pf: engine.PackedFrames, stats=None) -> torch.Tensor:
         """Fills this rank's D1 shard (its own tiles + the tiles peers push).  Stream-ordered barriers on
@@ -152,6 +154,14 @@ class SymmetricShardWorkspace:
         self.hdl.barrier(channel=0)
         engine.gram_l2_jobs(pf, self.jobs(), stats)
         self.hdl.barrier(channel=1)
+        halo = self.halo_rows()
+        if halo > 0:
+            # the halo rows are the first core rows of the next rank: one small peer copy over NVLink
+            # (fs rows) instead of fs-row MMA tiles that would waste 216 of their 256 rows
+            p, nxt = self.plan, self.rank + 1
+            src = self.hdl.get_buffer(nxt, (halo, self.ld), torch.float32)
+            lo = self.core(self.rank)[1] - p.r_lo
+            self.buf[lo:lo + halo].copy_(src)
         return self.D1()
 
 

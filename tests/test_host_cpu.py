@@ -174,8 +174,13 @@ def test_symmetric_shard_jobs_cover_every_needed_element_once(n, fs, stride, wor
                 blk += 1 if tri is None else (np.triu(np.ones((j["rows"], j["cols"]), dtype=np.int16), 1)).T
             pairs += j["rows"] * j["cols"] // (2 if j["symmetric"] else 1)
         work.append(pairs)
-    for c in cover:
-        assert c.min() == 1 and c.max() == 1
+    for r, c in enumerate(cover):                            # halo rows arrive by a peer copy of the next rank's first rows
+        ws = _WS(r)
+        core_rows = ws.core(r)[1] - plans[r].r_lo
+        assert c[:core_rows].min() == 1 and c[:core_rows].max() == 1
+        assert ws.halo_rows() == c.shape[0] - core_rows and (c[core_rows:] == 0).all()
+        if r + 1 < world:
+            assert plans[r + 1].r_lo == ws.core(r)[1] and ws.halo_rows() <= ws.core(r + 1)[1] - ws.core(r + 1)[0]
     assert max(work) <= 1.25 * (n * n / (2 * world)) + 300 * n           # balanced up to halos and tile rounding
 
 
