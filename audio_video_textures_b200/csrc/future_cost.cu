@@ -198,6 +198,105 @@ future_cost_fused_kernel(const float *__restrict__ D3, int64_t ld, int64_t m, fl
     if (blockIdx.x == 0 && threadIdx.x == 0) { info[0] = 0; info[1] = cur; }
 }
 
+// ------------------------------------------------------------------ multi-GPU fused future cost
+// Row-sharded version of future_cost_fused_kernel: every GPU runs one cooperative kernel over its own
+// rows; after each sweep the freshly computed row minima are PUSHED into every peer's copy of the
+// m vector (peer-mapped symmetric memory, plain stores over NVLink), the per-rank eps numerators are
+// pushed into per-rank slots, and a flag barrier (monotonic counters written by the peers, spun on
+// locally) closes the sweep.  This is the all-gather of the per-row minima the algorithm needs
+// (BASELINE.json north_star) done inside the kernel: ~10 us per sweep instead of a kernel launch, two
+// NCCL collectives and a host read of eps (~70 us).  Every rank adds the eps slots in rank order, so
+// all ranks take the same stop decision from bit-identical numbers.
+struct FcPeerArgs {
+    const float *D3;
+    int64_t ld, row0, rows, m, mpad;
+    float alpha, eps_stop;
+    int max_sweeps, rank, world;
+    unsigned int epoch_base;
+    float *mbuf[8];              // rank r's 3 * mpad floats
+    double *epsbuf[8];           // rank r's (max_sweeps + 1) * world slots
+    unsigned int *flags[8];      // rank r's `world` counters
+    double *eps_local;           // [max_sweeps + 1], zeroed: this rank's numerators (atomicAdd target)
+    double *eps_trail;           // [max_sweeps + 1] out: summed numerators
+    int *info;
+};
+
+__device__ __forceinline__ void fc_peer_exchange(cg::grid_group &grid, const FcPeerArgs &a, int step, bool with_eps) {
+    grid.sync();                                     // all local rows done, all pushes issued
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        const unsigned int target = a.epoch_base + (unsigned int)step + 1u;
+        __threadfence_system();                      // cumulative: orders every CTA's pushes before the flags
+        if (with_eps) {
+            const double mine = *reinterpret_cast<volatile double *>(a.eps_local + step);
+            for (int r = 0; r < a.world; ++r)
+                *reinterpret_cast<volatile double *>(a.epsbuf[r] + (int64_t)step * a.world + a.rank) = mine;
+            __threadfence_system();
+        }
+        for (int r = 0; r < a.world; ++r) *reinterpret_cast<volatile unsigned int *>(a.flags[r] + a.rank) = target;
+        const long long t0 = clock64();
+        for (int r = 0; r < a.world; ++r) {
+            while ((int)(*reinterpret_cast<volatile unsigned int *>(a.flags[a.rank] + r) - target) < 0) {
+                if (clock64() - t0 > 8000000000LL) {
+                    printf("avtex future_cost_fused_peer: rank %d timed out waiting for rank %d at step %d\n", a.rank, r, step);
+                    __trap();
+                }
+            }
+        }
+        __threadfence_system();
+    }
+    grid.sync();                                     // the gathered vector / eps slots may now be read
+}
+
+__global__ void __launch_bounds__(ST)
+future_cost_fused_peer_kernel(const FcPeerArgs a) {
+    __shared__ float fred[32];
+    __shared__ double dred[32];
+    cg::grid_group grid = cg::this_grid();
+    const float *local = a.mbuf[a.rank];
+    const int64_t row_end = a.row0 + a.rows;
+    auto push = [&](int buf, int64_t j, float v) {
+        for (int r = 0; r < a.world; ++r) a.mbuf[r][(int64_t)buf * a.mpad + j] = v;
+    };
+    for (int64_t j = a.row0 + blockIdx.x; j < row_end; j += gridDim.x) {
+        SweepAcc acc{INFINITY, 0.0};
+        sweep_row<false, false, false>(a.D3 + (j - a.row0) * a.ld, a.m, j, nullptr, nullptr, a.alpha, acc);
+        const float mn = block_reduce(acc.mn, INFINITY, OpMin(), fred);
+        if (threadIdx.x == 0) push(0, j, mn);
+    }
+    fc_peer_exchange(grid, a, 0, false);
+    int cur = 0, prev2 = -1;
+    for (int p = 1; p <= a.max_sweeps; ++p) {
+        const int out = 3 - cur - (prev2 < 0 ? (cur == 0 ? 1 : 0) : prev2);
+        const float *mp = local + (int64_t)cur * a.mpad;
+        const float *mp2 = prev2 < 0 ? nullptr : local + (int64_t)prev2 * a.mpad;
+        double e_blk = 0.0;
+        for (int64_t j = a.row0 + blockIdx.x; j < row_end; j += gridDim.x) {
+            SweepAcc acc{INFINITY, 0.0};
+            const float *row = a.D3 + (j - a.row0) * a.ld;
+            if (j == 0) sweep_row<false, false, false>(row, a.m, j, mp, mp2, a.alpha, acc);
+            else if (mp2 == nullptr) sweep_row<true, true, false>(row, a.m, j, mp, mp2, a.alpha, acc);
+            else sweep_row<true, true, true>(row, a.m, j, mp, mp2, a.alpha, acc);
+            const float mn = block_reduce(acc.mn, INFINITY, OpMin(), fred);
+            if (threadIdx.x == 0) push(out, j, mn);
+            e_blk += block_reduce(acc.e, 0.0, OpAdd<double>(), dred);
+        }
+        if (threadIdx.x == 0 && e_blk != 0.0) atomicAdd(a.eps_local + p, e_blk);
+        fc_peer_exchange(grid, a, p, true);
+        double num = 0.0;
+        for (int r = 0; r < a.world; ++r)
+            num += *reinterpret_cast<volatile double *>(a.epsbuf[a.rank] + (int64_t)p * a.world + r);
+        if (blockIdx.x == 0 && threadIdx.x == 0) a.eps_trail[p] = num;
+        const float eps = (float)(num / ((double)a.m * (double)a.m));
+        if (!(eps > a.eps_stop)) {
+            if (blockIdx.x == 0 && threadIdx.x == 0) { a.info[0] = p; a.info[1] = cur; }
+            return;
+        }
+        prev2 = cur;
+        cur = out;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) { a.info[0] = 0; a.info[1] = cur; }
+}
+
 }  // namespace
 
 extern "C" int avtex_future_cost_sweep(const float *D3, int64_t ld, int64_t row0, int64_t rows, int64_t m,
@@ -252,6 +351,42 @@ extern "C" int avtex_future_cost_fused(const float *D3, int64_t ld, int64_t m, f
     void *args[] = {(void *)&D3, (void *)&ld, (void *)&m, (void *)&alpha, (void *)&eps_stop, (void *)&max_sweeps,
                     (void *)&mbuf, (void *)&mpad, (void *)&eps_trail, (void *)&info};
     AVTEX_CUDA(cudaLaunchCooperativeKernel((void *)future_cost_fused_kernel, dim3((unsigned)grid), dim3(ST), args, 0,
+                                           as_stream(stream)));
+    return 0;
+}
+
+extern "C" int avtex_future_cost_fused_peer(const float *D3, int64_t ld, int64_t row0, int64_t rows, int64_t m,
+                                            float alpha, float eps_stop, int max_sweeps, int rank, int world,
+                                            float *const *h_mbuf, int64_t mpad, double *const *h_epsbuf,
+                                            unsigned int *const *h_flags, unsigned int epoch_base,
+                                            double *eps_local, double *eps_trail, int *info, int device,
+                                            void *stream) {
+    AVTEX_ENTER(device);
+    AVTEX_REQUIRE(world >= 1 && world <= 8 && rank >= 0 && rank < world, "future_cost_fused_peer: bad rank %d / world %d", rank, world);
+    AVTEX_REQUIRE(m >= 2 && rows >= 1 && row0 >= 0 && row0 + rows <= m && ld >= m && mpad >= m && mpad % 4 == 0 &&
+                      max_sweeps >= 1,
+                  "future_cost_fused_peer: bad shape row0=%lld rows=%lld m=%lld", (long long)row0, (long long)rows, (long long)m);
+    FcPeerArgs a;
+    a.D3 = D3; a.ld = ld; a.row0 = row0; a.rows = rows; a.m = m; a.mpad = mpad;
+    a.alpha = alpha; a.eps_stop = eps_stop; a.max_sweeps = max_sweeps; a.rank = rank; a.world = world;
+    a.epoch_base = epoch_base;
+    for (int r = 0; r < 8; ++r) {
+        a.mbuf[r] = r < world ? h_mbuf[r] : nullptr;
+        a.epsbuf[r] = r < world ? h_epsbuf[r] : nullptr;
+        a.flags[r] = r < world ? h_flags[r] : nullptr;
+    }
+    a.eps_local = eps_local; a.eps_trail = eps_trail; a.info = info;
+    int sms = 0, cc = 0, per_sm = 0, coop = 0;
+    if (int rc = avtex_device_info(device, &sms, &cc)) return rc;
+    AVTEX_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device));
+    AVTEX_REQUIRE(coop != 0, "future_cost_fused_peer: device does not support cooperative launch");
+    AVTEX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, future_cost_fused_peer_kernel, ST, 0));
+    AVTEX_REQUIRE(per_sm >= 1, "future_cost_fused_peer: kernel does not fit on an SM");
+    if (per_sm > 4) per_sm = 4;
+    int64_t grid = (int64_t)sms * per_sm;
+    if (grid > rows) grid = rows;
+    void *args[] = {(void *)&a};
+    AVTEX_CUDA(cudaLaunchCooperativeKernel((void *)future_cost_fused_peer_kernel, dim3((unsigned)grid), dim3(ST), args, 0,
                                            as_stream(stream)));
     return 0;
 }

@@ -165,6 +165,58 @@ class SymmetricShardWorkspace:
         return self.D1()
 
 
+class PeerFutureCost:
+    """Symmetric-memory workspace + driver of avtex_future_cost_fused_peer: the whole row-sharded
+    future-cost iteration in one cooperative kernel per GPU, exchanging the row minima by peer stores."""
+    MAX_SWEEPS = 254
+
+    def __init__(self, m: int, rank: int, world: int, device, group=None):
+        import torch.distributed._symmetric_memory as symm_mem
+        self.m, self.rank, self.world = m, rank, world
+        self.mpad = (m + 31) // 32 * 32
+        self.n_m = 6 * self.mpad * 4                                   # two sets of three fp32 vectors
+        self.n_eps = (self.MAX_SWEEPS + 1) * world * 8
+        total = self.n_m + self.n_eps + 256
+        group = dist.group.WORLD if group is None else group
+        self.buf = symm_mem.empty((total,), dtype=torch.uint8, device=device)
+        self.buf.zero_()
+        self.hdl = symm_mem.rendezvous(self.buf, group.group_name)
+        self.hdl.barrier(channel=0)
+        self.base = [int(p) for p in self.hdl.buffer_ptrs]
+        self.calls = 0
+        self.device = device
+
+    def run(self, D3_own: torch.Tensor, row0: int, alpha: float = 0.997, verbose: bool = False):
+        import ctypes as C
+        import numpy as np
+        from . import _lib
+        rows = D3_own.shape[0]
+        parity = self.calls % 2
+        arr = C.c_void_p * self.world
+        mptr = arr(*[b + parity * 3 * self.mpad * 4 for b in self.base])
+        eptr = arr(*[b + self.n_m for b in self.base])
+        fptr = arr(*[b + self.n_m + self.n_eps for b in self.base])
+        eps_local = torch.zeros(self.MAX_SWEEPS + 1, dtype=torch.float64, device=self.device)
+        trail = torch.zeros(self.MAX_SWEEPS + 1, dtype=torch.float64, device=self.device)
+        info = torch.zeros(2, dtype=torch.int32, device=self.device)
+        epoch = (self.calls * (self.MAX_SWEEPS + 2)) & 0xFFFFFFFF
+        _lib.call("avtex_future_cost_fused_peer", _lib.ptr(D3_own), D3_own.stride(0), row0, rows, self.m,
+                  C.c_float(engine._f32(alpha)), C.c_float(np.float32(engine.F32_EPS_STOP)), self.MAX_SWEEPS,
+                  self.rank, self.world, mptr, self.mpad, eptr, fptr, C.c_uint(epoch), _lib.ptr(eps_local),
+                  _lib.ptr(trail), _lib.ptr(info), engine._dev(D3_own), engine._stream(D3_own))
+        self.calls += 1
+        n_sweeps, idx = (int(v) for v in info.cpu())
+        if n_sweeps == 0:
+            raise RuntimeError("future cost did not converge")
+        m_all = self.buf[:self.n_m].view(torch.float32)
+        off = (parity * 3 + idx) * self.mpad
+        eps = [float(np.float32(v / (float(self.m) ** 2))) for v in trail[1:n_sweeps + 1].cpu()]
+        if verbose:
+            for e in eps:
+                print("Eps:", f"tensor({e:.4f})")
+        return engine.FutureCostResult(m_all[off:off + self.m], n_sweeps, eps, n_sweeps + 1)
+
+
 @dataclass
 class ShardResult:
     plan: ShardPlan
@@ -184,7 +236,8 @@ class ShardResult:
 def classic_sharded(frames: torch.Tensor, filter_size: int, stride: int, rank: int, world: int,
                     p: float = 0.7, alpha: float = 0.997, sigma_factor=None, threshold=None, group=None,
                     packed: engine.PackedFrames | None = None,
-                    workspace: SymmetricShardWorkspace | None = None) -> ShardResult:
+                    workspace: SymmetricShardWorkspace | None = None,
+                    peer_fc: PeerFutureCost | None = None) -> ShardResult:
     """Distance + filter + converged future cost (+ sigma3 / P3 / P3_new when sigma_factor is given) for
     this rank's rows.  `frames`: the full [N, ...] uint8 clip on this rank's device.  With a
     SymmetricShardWorkspace the distance stage uses the symmetry across ranks (peer pushes over NVLink);
@@ -201,10 +254,15 @@ def classic_sharded(frames: torch.Tensor, filter_size: int, stride: int, rank: i
     D2, D3 = engine.diag_filter(D1, filter_size, stride, p=p, m=plan.m, a0=plan.a0,
                                 rows_out=plan.a1h - plan.a0, in_row0=plan.r_lo)
     own = plan.a1 - plan.a0
-    fc = engine.future_cost(D3[:own], alpha, row0=plan.a0, m=plan.m, exchange=make_exchange(plan, group),
-                            pad_to=plan.padded)
+    if peer_fc is not None and world > 1:
+        fc = peer_fc.run(D3[:own], plan.a0, alpha)         # all sweeps + exchanges inside one kernel per GPU
+        n_fc_launches = 1
+    else:
+        fc = engine.future_cost(D3[:own], alpha, row0=plan.a0, m=plan.m, exchange=make_exchange(plan, group),
+                                pad_to=plan.padded)
+        n_fc_launches = fc.passes
     res = ShardResult(plan, D1, D2, D3, None, fc.n_sweeps, fc.eps_trail)
-    res.launches = 1 + 1 + 1 + fc.passes + 1
+    res.launches = 1 + 1 + 1 + n_fc_launches + 1
     res.D3_new = engine.future_cost_finalize(D3, fc.mvec, alpha, row0=plan.a0, m=plan.m)
     if sigma_factor is not None:
         stats = engine.sum_nnz(res.D3_new[:own])

@@ -172,9 +172,10 @@ def run_ours(args):
     peaks = load_peaks()
     gram_ms, step_ms = [], []
     state = {}
-    workspace = None
+    workspace = peer_fc = None
     if world > 1 and not args.no_symmetric:
         workspace = avdist.SymmetricShardWorkspace(n, fs, stride, rank, world, dev)
+        peer_fc = avdist.PeerFutureCost(avdist.plan_shards(n, fs, stride, world, rank).m, rank, world, dev)
 
     def one_step(timed: bool):
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
@@ -194,7 +195,8 @@ def run_ours(args):
             state.update(D1=D1, D3n=D3n, sweeps=fc.n_sweeps, m=D3.shape[0], rows=n)
         else:
             ev[1].record()
-            res = avdist.classic_sharded(frames, fs, stride, rank, world, packed=pf, workspace=workspace)
+            res = avdist.classic_sharded(frames, fs, stride, rank, world, packed=pf, workspace=workspace,
+                                         peer_fc=peer_fc)
             ev[2].record()       # (gram is the first kernel after ev[1]; the sharded call is timed as a whole)
             launches = res.launches
             state.update(D3n=res.D3_new, sweeps=res.n_sweeps, m=res.plan.m, rows=res.plan.r_hi - res.plan.r_lo)
@@ -274,7 +276,8 @@ def run_ours(args):
                    "name": args.workload, "l2": "256 MB L2 flush between timed steps",
                    "sharding": "single GPU" if world == 1 else
                    (f"rows over {world} ranks, N=5000*sqrt(G)" if args.workload == "c2" else f"rows over {world} ranks") +
-                   ("" if world == 1 or args.no_symmetric else "; symmetric Gram, transposed tiles pushed to peer shards over NVLink")},
+                   ("" if world == 1 or args.no_symmetric else "; symmetric Gram, transposed tiles pushed to peer shards over NVLink; future cost "
+                                                                 "fused with its all-gather (peer stores + flag barrier)")},
         "gpu_launches": launches, "wall_s": wall,
     }
     if world == 1:

@@ -165,6 +165,21 @@ AVTEX_API int avtex_future_cost_sweep(const float *D3, int64_t ld, int64_t row0,
 AVTEX_API int avtex_future_cost_fused(const float *D3, int64_t ld, int64_t m, float alpha, float eps_stop,
                             int max_sweeps, float *mbuf, int64_t mpad, double *eps_trail, int *info,
                             int device, void *stream);
+/* Row-sharded form of avtex_future_cost_fused (one cooperative kernel per GPU, launched on every rank):
+ * this rank owns rows [row0, row0+rows) of D3.  After each sweep the kernel pushes its row minima into every
+ * rank's m buffer and its eps numerator into every rank's slot array through PEER-MAPPED pointers
+ * (h_mbuf[r], h_epsbuf[r], h_flags[r]: rank r's buffers as mapped in this process, e.g. a torch
+ * symmetric-memory allocation; 3*mpad floats, (max_sweeps+1)*world doubles, world uint32), then
+ * spins on the flag counters its peers write: the per-sweep all-gather and eps all-reduce happen inside the
+ * kernel over NVLink.  Flags are monotonic: pass epoch_base = (calls so far) * (max_sweeps + 2), identical on
+ * all ranks, and zero the flag/eps buffers once at allocation.  eps_local: [max_sweeps+1] doubles zeroed by
+ * the caller (local scratch); eps_trail / info as in avtex_future_cost_fused; the result vector is
+ * h_mbuf[rank] + info[1]*mpad.  world <= 8. */
+AVTEX_API int avtex_future_cost_fused_peer(const float *D3, int64_t ld, int64_t row0, int64_t rows, int64_t m,
+                                 float alpha, float eps_stop, int max_sweeps, int rank, int world,
+                                 float *const *h_mbuf, int64_t mpad, double *const *h_epsbuf,
+                                 unsigned int *const *h_flags, unsigned int epoch_base, double *eps_local,
+                                 double *eps_trail, int *info, int device, void *stream);
 /* D3_new[j,:] = D3[j,:] + fl(alpha * mvec)  (j >= 1),  row 0 copied.  sum/nnz nullable.
  * replaces: the materialised D3_new of classic/q_learning.py:48 at convergence. */
 AVTEX_API int avtex_future_cost_finalize(const float *D3, int64_t ld, int64_t row0, int64_t rows, int64_t m,
