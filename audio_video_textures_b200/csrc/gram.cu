@@ -184,6 +184,10 @@ __device__ __forceinline__ void epilogue_tile(const GramArgs &args, const GramJo
     int64_t rows_here = row_end - r0;                              // valid rows of this warp's 32
     if (rows_here > 32) rows_here = 32;
     const bool sym = job.symmetric != 0;
+    // every stored element is counted once; D and DT hold the same values, so when both exist the
+    // direct loop counts with weight 2 and the transposed loop not at all (a diagonal entry is 0)
+    const int w_direct = (job.D != nullptr) ? ((job.DT != nullptr) ? 2 : 1) : 0;
+    const int w_trans = (job.D != nullptr) ? 0 : 1;
 #pragma unroll 1
     for (int cc = 0; cc < BN / 32; ++cc) {
         uint32_t g[32];
@@ -197,43 +201,69 @@ __device__ __forceinline__ void epilogue_tile(const GramArgs &args, const GramJo
         if (cbase >= col_end || rows_here <= 0) continue;
         if (sym && cbase + 31 < r0) continue;                     // whole chunk below the diagonal for this warp
         const uint32_t nc_lane = (cbase + lane < col_end) ? (uint32_t)__ldg(args.sqnorm + cbase + lane) : 0u;
+        // warp-uniform: all 32 x 32 elements are valid and (symmetric) strictly above the diagonal ->
+        // no per-element predicates (the per-element branches of the general path were the critical path
+        // of the whole kernel at K = 12288: the epilogue, not the MMAs, set the tile time)
+        const bool interior = (rows_here == 32) && (cbase + 32 <= col_end) && (!sym || r0 + 31 < cbase);
         __syncwarp();                                             // previous chunk's tile reads are finished
-        // sigma statistics: fp32 / int partials per 32-element chunk, promoted to fp64 once per chunk
-        // (a per-element DFMA chain made the epilogue, not the MMAs, the critical path at K = 12288)
-        float cs = 0.f;
+        float cs = 0.f;                                           // fp32 / int partials per chunk, fp64 once per chunk
         int cz = 0;
         float *dt = (job.DT != nullptr) ? job.DT + (cbase - job.dt_row0) * job.ldt + r : nullptr;
+        if (interior) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-            const uint32_t nc = __shfl_sync(0xffffffffu, nc_lane, j);
-            const uint32_t d2 = nr + nc - 2u * g[j];              // exact mod 2^32
-            const float d = __fsqrt_rn(__uint2float_rn(d2));
-            tile[lane * EPI_PITCH + j] = d;
-            const int64_t c = cbase + j;
-            if (dt != nullptr && r_ok && c < col_end && (!sym || r < c)) {
-                dt[j * job.ldt] = d;                              // transposed store: coalesced across the warp
-                cs += d;
-                cz += (d != 0.f);
+            for (int j = 0; j < 32; ++j) {
+                const uint32_t nc = __shfl_sync(0xffffffffu, nc_lane, j);
+                const float d = __fsqrt_rn(__uint2float_rn(nr + nc - 2u * g[j]));      // d^2 exact mod 2^32
+                tile[lane * EPI_PITCH + j] = d;
+                if (dt != nullptr) {
+                    *dt = d;                                      // transposed store: one 128 B line per warp
+                    dt += job.ldt;
+                }
+                if (w_trans) { cs += d; cz += (d != 0.f); }
             }
-        }
-        __syncwarp();
-        if (job.D != nullptr) {
-            const int64_t c = cbase + lane;                       // this lane's column for the row stores
-            const bool c_ok = c < col_end;
-            float *dst = job.D + (r0 - job.d_row0) * job.ldd + c;
-#pragma unroll 8
-            for (int i = 0; i < 32; ++i) {
-                if (i < rows_here && c_ok && (!sym || r0 + i <= c)) {
+            __syncwarp();
+            if (job.D != nullptr) {
+                float *dst = job.D + (r0 - job.d_row0) * job.ldd + cbase + lane;
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
                     const float d = tile[i * EPI_PITCH + lane];
-                    dst[i * job.ldd] = d;
+                    *dst = d;                                     // direct store: one 128 B line per warp
+                    dst += job.ldd;
                     cs += d;
                     cz += (d != 0.f);
                 }
             }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const uint32_t nc = __shfl_sync(0xffffffffu, nc_lane, j);
+                const float d = __fsqrt_rn(__uint2float_rn(nr + nc - 2u * g[j]));
+                tile[lane * EPI_PITCH + j] = d;
+                const int64_t c = cbase + j;
+                if (dt != nullptr && r_ok && c < col_end && (!sym || r < c)) {
+                    dt[j * job.ldt] = d;
+                    if (w_trans) { cs += d; cz += (d != 0.f); }
+                }
+            }
+            __syncwarp();
+            if (job.D != nullptr) {
+                const int64_t c = cbase + lane;
+                const bool c_ok = c < col_end;
+                float *dst = job.D + (r0 - job.d_row0) * job.ldd + c;
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    if (i < rows_here && c_ok && (!sym || r0 + i <= c)) {
+                        const float d = tile[i * EPI_PITCH + lane];
+                        dst[i * job.ldd] = d;
+                        if (!sym || r0 + i < c || job.DT == nullptr) { cs += d; cz += (d != 0.f); }
+                    }
+                }
+            }
         }
         if (job.count_stats) {
-            st.s += (double)cs;
-            st.z += (unsigned long long)cz;
+            const int w = (job.D != nullptr) ? w_direct : 1;
+            st.s += (double)(w * cs);
+            st.z += (unsigned long long)(w * cz);
         }
     }
 }
