@@ -345,8 +345,7 @@ extern "C" int avtex_future_cost_fused(const float *D3, int64_t ld, int64_t m, f
     AVTEX_REQUIRE(coop != 0, "future_cost_fused: device does not support cooperative launch");
     AVTEX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, future_cost_fused_kernel, ST, 0));
     AVTEX_REQUIRE(per_sm >= 1, "future_cost_fused: kernel does not fit on an SM");
-    if (per_sm > 4) per_sm = 4;
-    int64_t grid = (int64_t)sms * per_sm;
+    int64_t grid = (int64_t)sms * per_sm;              // full occupancy: the sweeps are HBM/L2 streaming
     if (grid > m) grid = m;
     void *args[] = {(void *)&D3, (void *)&ld, (void *)&m, (void *)&alpha, (void *)&eps_stop, (void *)&max_sweeps,
                     (void *)&mbuf, (void *)&mpad, (void *)&eps_trail, (void *)&info};
@@ -382,7 +381,6 @@ extern "C" int avtex_future_cost_fused_peer(const float *D3, int64_t ld, int64_t
     AVTEX_REQUIRE(coop != 0, "future_cost_fused_peer: device does not support cooperative launch");
     AVTEX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, future_cost_fused_peer_kernel, ST, 0));
     AVTEX_REQUIRE(per_sm >= 1, "future_cost_fused_peer: kernel does not fit on an SM");
-    if (per_sm > 4) per_sm = 4;
     int64_t grid = (int64_t)sms * per_sm;
     if (grid > rows) grid = rows;
     void *args[] = {(void *)&a};

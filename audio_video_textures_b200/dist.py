@@ -231,6 +231,7 @@ class ShardResult:
     P3_new: torch.Tensor | None = None
     counts: torch.Tensor | None = None
     launches: int = 0
+    stage_ms: dict | None = None          # CUDA-event stage times when AVTEX_DIST_TIMING=1
 
 
 def classic_sharded(frames: torch.Tensor, filter_size: int, stride: int, rank: int, world: int,
@@ -242,18 +243,32 @@ def classic_sharded(frames: torch.Tensor, filter_size: int, stride: int, rank: i
     this rank's rows.  `frames`: the full [N, ...] uint8 clip on this rank's device.  With a
     SymmetricShardWorkspace the distance stage uses the symmetry across ranks (peer pushes over NVLink);
     without one every rank computes its full row block locally."""
+    import os
+    timing = os.environ.get("AVTEX_DIST_TIMING") == "1"
+    marks = []
+
+    def mark(name):
+        if timing:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            marks.append((name, ev))
+
     n = frames.shape[0]
     plan = plan_shards(n, filter_size, stride, world, rank)
+    mark("start")
     pf = engine.pack_frames(frames) if packed is None else packed
+    mark("norms")
     if not pf.exact_ok:
         raise engine._lib.AvtexError(f"sharded path needs byte frames inside the Gram domain: {pf.reason}")
     if workspace is not None and world > 1:
         D1 = workspace.gram(pf)                            # symmetric across ranks: transposed tiles pushed to peers
     else:
         D1 = engine.gram_l2(pf, plan.r_lo, plan.r_hi - plan.r_lo, symmetric=False)
+    mark("gram")
     D2, D3 = engine.diag_filter(D1, filter_size, stride, p=p, m=plan.m, a0=plan.a0,
                                 rows_out=plan.a1h - plan.a0, in_row0=plan.r_lo)
     own = plan.a1 - plan.a0
+    mark("filter")
     if peer_fc is not None and world > 1:
         fc = peer_fc.run(D3[:own], plan.a0, alpha)         # all sweeps + exchanges inside one kernel per GPU
         n_fc_launches = 1
@@ -263,7 +278,12 @@ def classic_sharded(frames: torch.Tensor, filter_size: int, stride: int, rank: i
         n_fc_launches = fc.passes
     res = ShardResult(plan, D1, D2, D3, None, fc.n_sweeps, fc.eps_trail)
     res.launches = 1 + 1 + 1 + n_fc_launches + 1
+    mark("future_cost")
     res.D3_new = engine.future_cost_finalize(D3, fc.mvec, alpha, row0=plan.a0, m=plan.m)
+    mark("finalize")
+    if timing:
+        torch.cuda.synchronize()
+        res.stage_ms = {b[0]: a[1].elapsed_time(b[1]) for a, b in zip(marks[:-1], marks[1:])}
     if sigma_factor is not None:
         stats = engine.sum_nnz(res.D3_new[:own])
         if world > 1:

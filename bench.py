@@ -199,6 +199,8 @@ def run_ours(args):
                                          peer_fc=peer_fc)
             ev[2].record()       # (gram is the first kernel after ev[1]; the sharded call is timed as a whole)
             launches = res.launches
+            if res.stage_ms is not None and rank == 0 and timed:
+                print("stage_ms", {k: round(v, 3) for k, v in res.stage_ms.items()}, file=sys.stderr)
             state.update(D3n=res.D3_new, sweeps=res.n_sweeps, m=res.plan.m, rows=res.plan.r_hi - res.plan.r_lo)
         ev[3].record()
         torch.cuda.synchronize()
