@@ -48,10 +48,17 @@ def compute_D1(
     if feats != "RGB":
         raise NotImplementedError(
             f"feats={feats!r}: only the RGB branch of compute_D1 is implemented (SURVEY.md §2.1 row 1)")
-    x = _to_device(frames)
-    if x.dtype not in (torch.uint8, torch.float32):
-        x = x.float()
-    stats = engine.new_stats(x.device)
-    D1, _ = engine.pairwise_l2(x, stats=stats)
+    if not torch.cuda.is_available():
+        raise RuntimeError("audio_video_textures_b200 needs a CUDA device (B200); there is no CPU path")
+    stats = engine.new_stats(torch.device("cuda", torch.cuda.current_device()))
+    streamed = engine.pairwise_l2_from_host(frames, stats=stats) if not frames.is_cuda else None
+    if streamed is not None and streamed[1].exact_ok:      # uint8 host frames: Gram overlapped with the H2D copy
+        D1 = streamed[0]
+    else:
+        x = _to_device(frames)
+        if x.dtype not in (torch.uint8, torch.float32):
+            x = x.float()
+        stats.zero_()
+        D1, _ = engine.pairwise_l2(x, stats=stats)
     P1, _, sigma, _ = tail(D1, sigma_factor, stats)
     return D1, P1, sigma

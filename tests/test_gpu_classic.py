@@ -102,6 +102,23 @@ def test_gram_distance_exact_and_within_tolerance(eng, name):
     assert torch.equal(Dh, Dd.cpu())                         # byte frames: both paths give the exact d^2
 
 
+def test_streamed_host_frames_equal_resident(eng):
+    """compute_D1 on uint8 HOST frames (chunked H2D overlapped with the Gram jobs) == device-resident path."""
+    from audio_video_textures_b200.classic.computeD1 import compute_D1
+    from audio_video_textures_b200.synth import synth_video
+    video = synth_video(1300, 16, 16, seed=4)
+    f = torch.tensor(4.5)
+    for host in (video, video.pin_memory()):
+        D1h, P1h, s1h = compute_D1(host, f, "RGB")
+        D1d, P1d, s1d = compute_D1(video.cuda(), f, "RGB")
+        assert torch.equal(D1h, D1d)
+        np.testing.assert_allclose(s1h.item(), s1d.item(), rtol=1e-6)
+        np.testing.assert_allclose(P1h.cpu().numpy(), P1d.cpu().numpy(), rtol=1e-5)
+    res = eng.pairwise_l2_from_host(video, chunks=3)
+    assert res is not None and torch.equal(res[0], D1d)
+    assert eng.pairwise_l2_from_host(video.float()) is None and eng.pairwise_l2_from_host(video[:100]) is None
+
+
 def test_gram_edge_shapes(eng):
     """Ragged N (not a multiple of the 128 x 256 tile), K not a multiple of 128, duplicate frames,
     a single K block, and N smaller than one tile."""
