@@ -43,6 +43,10 @@ WORKLOADS = {
     # measure the HBM-bound kernels (filter, sweep, finalize, probabilities) against the HBM roofline
     "hbm": dict(n=20000, h=64, w=64, m=1, fs=40, stride=1),
 }
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE gram_l2_s8_2cta_kernel launch at C2 from the committed
+# ncu capture (profiles/r01_launches_c2_v2.summary.txt: 2368 MB read + 75 MB written; operands are 753 MB,
+# D1 100 MB stays in L2)
+GRAM_DRAM_BYTES_C2 = 2.443e9
 METRIC = "frame-pairs/s (distance + temporal filter + converged future-cost)"
 L2_FLUSH_BYTES = 256 << 20
 
@@ -289,7 +293,7 @@ def run_ours(args):
         out["roofline"] = {
             "kernel": "gram_l2_s8_kernel (tcgen05 kind::i8, symmetric schedule)", "bound": "tensor",
             "achieved": ach, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": ach / peaks["bf16_tflops"],
-            "traffic": None, "ms": g_ms, "share_of_step": g_ms * len(gram_ms) / sum(step_ms),
+            "traffic": GRAM_DRAM_BYTES_C2 if args.workload == "c2" else None, "ms": g_ms, "share_of_step": g_ms * len(gram_ms) / sum(step_ms),
             "note": ("algorithmic flops 2*K*N^2 over the event-timed launch; the symmetric schedule executes "
                      "~half of them and kind::i8 runs at twice the bf16 rate, so frac is quoted against the "
                      f"measured bf16 peak from {peaks['source']} and can exceed 1")}
