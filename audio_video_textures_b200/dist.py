@@ -37,7 +37,7 @@ class ShardPlan:
 
 def plan_shards(n: int, filter_size: int, stride: int, world: int, rank: int) -> ShardPlan:
     m = engine.filtered_size(n, filter_size, stride)
-    shard = -(-m // world)
+    shard = (-(-m // world) + 3) // 4 * 4          # multiple of 4 rows: keeps every shard's D1 rows 16-byte aligned
     a0 = rank * shard
     a1 = min(m, a0 + shard)
     if a0 >= m:
@@ -127,9 +127,10 @@ class SymmetricShardWorkspace:
         mine = dict(D=self.ptrs[me], d_row0=p.r_lo, ldd=self.ld)
         out = [dict(row0=lo, rows=hi - lo, col0=lo, cols=hi - lo, symmetric=1, count_stats=1,
                     DT=self.ptrs[me], dt_row0=p.r_lo, ldt=self.ld, **mine)]
-        for other in range(self.world):
-            if other == me:
-                continue
+        # peers are visited in rotated order (me+1, me+2, ...): at any moment every rank pushes into a
+        # DIFFERENT destination, instead of all ranks hammering rank 0's NVLink ingress first, then rank 1's...
+        for step in range(1, self.world):
+            other = (me + step) % self.world
             olo, ohi = self.core(other)
             peer = dict(DT=self.ptrs[other], dt_row0=self.plans[other].r_lo, ldt=self.ld)
             if me < other:                                  # my rows x the first half of the peer's columns
