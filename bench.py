@@ -44,9 +44,9 @@ WORKLOADS = {
     "hbm": dict(n=20000, h=64, w=64, m=1, fs=40, stride=1),
 }
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE gram_l2_s8_2cta_kernel launch at C2 from the committed
-# ncu capture (profiles/r01_launches_c2_v2.summary.txt: 2368 MB read + 75 MB written; operands are 753 MB,
-# D1 100 MB stays in L2)
-GRAM_DRAM_BYTES_C2 = 2.443e9
+# ncu capture (profiles/r01_launches_c2_final.summary.txt: 1699 MB read + 73 MB written; operands are 753 MB,
+# the 100 MB D1 mostly stays in L2)
+GRAM_DRAM_BYTES_C2 = 1.771e9
 METRIC = "frame-pairs/s (distance + temporal filter + converged future-cost)"
 L2_FLUSH_BYTES = 256 << 20
 
