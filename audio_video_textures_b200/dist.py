@@ -63,6 +63,27 @@ def load_frames_sharded(host_frames: torch.Tensor, rank: int, world: int, device
     return full[:n]
 
 
+def pack_frames_sharded(frames: torch.Tensor, rank: int, world: int, group=None) -> engine.PackedFrames:
+    """K0 for the replicated clip: every rank computes the norms of 1/G of the frames and the [N] int64 vector is
+    all-gathered (113 KB at N = 14144) instead of every rank reading all N*K bytes again."""
+    x = frames.reshape(frames.shape[0], -1)
+    n, k = x.shape
+    if world == 1 or x.dtype != torch.uint8 or x.stride(0) % 16 != 0 or x.data_ptr() % 16 != 0 or x.stride(1) != 1:
+        return engine.pack_frames(frames)
+    per = -(-n // world)
+    sqnorm = torch.zeros(per * world, dtype=torch.int64, device=x.device)
+    flags = torch.zeros(2, dtype=torch.int64, device=x.device)
+    lo, hi = rank * per, min(n, (rank + 1) * per)
+    if hi > lo:
+        engine.frame_norms_rows(x, lo, hi - lo, sqnorm, flags)
+    dist.all_gather_into_tensor(sqnorm, sqnorm[rank * per:(rank + 1) * per], group=group)
+    dist.all_reduce(flags, op=dist.ReduceOp.MAX, group=group)
+    pf = engine.PackedFrames(x, sqnorm[:n], k, flags, signed=False)
+    if (k + 127) // 128 * 128 * 128 * 128 < engine.GRAM_MAX_SQNORM:
+        pf._checked = (True, "")
+    return pf
+
+
 def make_exchange(plan: ShardPlan, group=None):
     """Returns exchange(mvec, eps_buf): in-place all-gather of the per-row minima (each rank wrote
     its own rows of the padded vector) + all-reduce of the eps numerator."""
@@ -273,7 +294,7 @@ def classic_sharded(frames: torch.Tensor, filter_size: int, stride: int, rank: i
     n = frames.shape[0]
     plan = plan_shards(n, filter_size, stride, world, rank)
     mark("start")
-    pf = engine.pack_frames(frames) if packed is None else packed
+    pf = pack_frames_sharded(frames, rank, world, group) if packed is None else packed
     mark("norms")
     if not pf.exact_ok:
         raise engine._lib.AvtexError(f"sharded path needs byte frames inside the Gram domain: {pf.reason}")

@@ -147,6 +147,16 @@ def pack_frames(frames: torch.Tensor) -> PackedFrames:
     return pf
 
 
+def frame_norms_rows(frames_u8: torch.Tensor, row0: int, rows: int, sqnorm: torch.Tensor, flags: torch.Tensor):
+    """K0 on a row range of raw uint8 frames [N, K] (row pitch multiple of 16): fills sqnorm[row0:row0+rows]
+    and raises flags[1] to the maximum centred norm.  Used by the sharded path, where each rank computes only
+    its own slice of the norms."""
+    part = frames_u8[row0:row0 + rows]
+    _lib.call("avtex_frame_norms_u8", _lib.ptr(part), rows, frames_u8.shape[1], frames_u8.stride(0),
+              C.c_void_p(sqnorm.data_ptr() + 8 * row0), C.c_void_p(flags.data_ptr() + 8), _dev(frames_u8),
+              _stream(frames_u8))
+
+
 def gram_l2(pf: PackedFrames, row0: int = 0, rows: int | None = None, symmetric: bool | None = None,
             stats: torch.Tensor | None = None, out: torch.Tensor | None = None) -> torch.Tensor:
     """K1 on tensor cores.  Returns D[rows, N] for global rows [row0, row0+rows)."""

@@ -30,6 +30,8 @@ def main():
     rowptr, colidx = avd.gather_survivors(res)
     # single-GPU result on every rank
     pf = engine.pack_frames(frames)
+    pfs = avd.pack_frames_sharded(frames, rank, world)
+    assert torch.equal(pfs.sqnorm, pf.sqnorm) and pfs.exact_ok == pf.exact_ok
     D1 = engine.gram_l2(pf)
     D2, D3 = engine.diag_filter(D1, fs, stride, p=0.7)
     fc = engine.future_cost(D3)
