@@ -96,29 +96,38 @@ def audio_video_texture(args, P, frames, output_video_folder, output_video_folde
 
 
 def main(args, video_name: str):
-    """Hot-path part of the reference `main` (:244-454): for each sigma factor run D1 -> D2 ->
-    future cost -> walk.  D1/D2/D3 do not depend on sigma, so they are computed once and only the
-    sigma/probability tails are re-evaluated (the reference recomputes everything 5 times)."""
+    """Hot-path part of the reference `main` (:244-454): for each sigma factor of the sweep (:250) produce
+    P3_new and walk it.  D1, D2 and the converged future cost do not depend on sigma, so they are computed
+    ONCE; per sigma factor only sigma3 / P3 / P3_new and the walk are re-evaluated (the reference recomputes
+    everything five times, :265-284).  Prints the reference's `Eps:` / `Non Zero in P3:` / `Frames list:` lines.
+    Returns dict(sigmas, jump_counts, sequences)."""
     from .utils import read_data
     input_frames, video, args.fps, audio, args.sr, _ = read_data(args, video_name)
+    if args.feats != "RGB":
+        raise NotImplementedError("only -f RGB is on the hot path")
+    frames = input_frames if input_frames.is_cuda else input_frames.cuda(non_blocking=True)
+    D1, used = engine.pairwise_l2(frames if frames.dtype in (torch.uint8, torch.float32) else frames.float())
+    stride = 1 if args.model_type in (1, 2) else args.stride            # video_textures.py:276-283
+    D2, D3 = engine.diag_filter(D1, args.filter_size, stride, p=0.7)
+    fc = engine.future_cost_fused(D3, 0.997, verbose=True)
+    stats = engine.new_stats(D3.device)
+    D3_new = engine.future_cost_finalize(D3, fc.mvec, 0.997, stats=stats)
+    total, nnz = engine.read_stats(stats)
     jump_counts, new_sigmas, sequences = [], [], []
     for value in torch.tensor(SIGMAS, dtype=torch.float32):
-        D1, P1, sigma = compute_D1(input_frames, value, args.feats, audio=audio, sr=args.sr, fps=args.fps,
-                                   slow=args.slow, batch_size=args.batch_size)
-        if args.model_type in (1, 2):
-            D2, P2, sigma, binomial_filter = compute_D2(D1, value, filter_size=args.filter_size)
-        else:
-            D2, P2, sigma, binomial_filter = compute_D2(D1, value, filter_size=args.filter_size,
-                                                        stride=args.stride)
-        D3, P3, P3_new, sigma = q_learning(D2, value, thresholding=args.threshold)
-        new_sigmas.append(sigma)
+        sigma = engine.sigma_from_stats(total, nnz, value)
+        P3, P3_new, counts = engine.transition_probs(D3_new, sigma, threshold=args.threshold, want_P=False,
+                                                     want_counts=True)
+        print("Non Zero in P3:", int(counts[0].item()))
+        new_sigmas.append(float(sigma))
         out_dir = None
         if getattr(args, "write_frames", False):
-            out_dir = os.path.join(args.results_folder, "{}_{}_{:.4f}".format(video_name, args.model_type,
-                                                                              sigma.item()))
-        jump_counts.append(audio_video_texture(args, P3_new, video, out_dir, None, audio, ""))
+            out_dir = os.path.join(args.results_folder, "{}_{}_{:.4f}".format(video_name, args.model_type, float(sigma)))
+        jump_counts.append(audio_video_texture(args, engine.csr_from_matrix(P3_new, counts), video, out_dir, None,
+                                               audio, ""))
         sequences.append(audio_video_texture.last_frames)
-    return dict(sigmas=[float(s) for s in new_sigmas], jump_counts=jump_counts, sequences=sequences)
+    return dict(sigmas=new_sigmas, jump_counts=jump_counts, sequences=sequences, n_sweeps=fc.n_sweeps,
+                distance_path=used)
 
 
 def build_parser() -> argparse.ArgumentParser:

@@ -360,3 +360,43 @@ def test_dropin_pipeline_end_to_end(eng, name, capsys):
     frames_out, jumps = texture_walk(P3n, m, int(g["fps"]), int(g["nvl"]), stride, fs)
     np.testing.assert_array_equal(np.array(frames_out), g["walk_frames"])
     assert jumps == int(g["walk_jump_count"]) and ql_mod.LAST["n_sweeps"] == int(g["ref_n_sweeps"])
+
+
+# ----------------------------------------------------------------------------- CLI orchestration
+@pytest.mark.parametrize("model_type,stride,n,seed", [(1, 1, 300, 3), (2, 2, 300, 3), (3, 4, 520, 5)])
+def test_cli_main_sigma_sweep_matches_oracle(eng, model_type, stride, n, seed, capsys):
+    """`video_textures.main` (the -m 1/2/3 entry point) on a synthetic clip: for every sigma factor of the
+    reference's sweep the emitted frame sequence equals the oracle's under the same numpy seed."""
+    from audio_video_textures_b200.classic import video_textures as vt
+    from audio_video_textures_b200.synth import synth_video
+    from oracle import classic as oc
+    h, w, fs, th, nvl = 8, 8, 16, 0.08, 2                       # clips screened offline for threshold margins
+    args = vt.build_parser().parse_args(
+        ["-m", str(model_type), "-fs", str(fs), "-stride", str(stride), "-t", str(th), "-nvl", str(nvl),
+         "--synthetic", f"{n},{h},{w},{seed}"])
+    video = synth_video(n, h, w, seed=seed)
+    D1 = oc.pairwise_l2(video.float())
+    eff_stride = 1 if model_type in (1, 2) else stride
+    sweep, checked = list(vt.SIGMAS), 0
+    try:
+        for value in sweep:                                   # one sigma factor per call: independent RNG streams
+            vt.SIGMAS[:] = [value]
+            np.random.seed(5)
+            res = vt.main(args, "synthetic")
+            out = capsys.readouterr().out
+            assert out.count("Frames list:") == 1 and "Eps:" in out and "Non Zero in P3:" in out
+            f = torch.tensor(value, dtype=torch.float32)
+            D2 = oc.compute_D2(D1, f, fs, eff_stride)[0]
+            D3n, P3, P3n, s3 = oc.q_learning(D2, f, thresholding=th)
+            np.testing.assert_allclose(res["sigmas"][0], float(s3), rtol=1e-5)
+            np.random.seed(5)
+            want, jumps = oc.walk(P3n, model_type, args.fps, nvl, stride, fs)
+            m_rows = P3.shape[0]
+            visited = sorted({r for f0 in want for r in (f0, min(f0 + stride, m_rows - 1)) if r < m_rows} | {100})
+            if oc.threshold_margin(P3, th, rows=visited) < 1e-5:
+                continue                                      # a visited row's survivor set hinges on an element at the cut
+            assert res["sequences"][0] == want and res["jump_counts"][0] == jumps
+            checked += 1
+    finally:
+        vt.SIGMAS[:] = sweep
+    assert checked >= 2

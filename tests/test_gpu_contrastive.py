@@ -116,3 +116,18 @@ def test_synthesis_medium_against_oracle(eng):
                      q_start=10)
     assert got["q_ids"] == want["q_ids"] and got["frame_ids"] == want["frame_ids"]
     assert got["jump_count"] == want["jump_count"] and got["nz_counts"] == want["nz_counts"]
+
+
+def test_cli_main_synthesis_mode(eng, capsys):
+    """`contrastive.main -e -th -temp -mbs` on synthetic embeddings: same windows as the oracle."""
+    from audio_video_textures_b200.contrastive import main as cm
+    from audio_video_textures_b200.synth import synth_embeddings
+    from oracle import contrastive as oc
+    args = cm.build_parser().parse_args("-e -th 0.3 -temp 0.1 -mbs 100 -nvl 3 --synthetic 400,64,2 --seed 9".split())
+    res = cm.main(args)
+    assert "Chosen windows:" in capsys.readouterr().out
+    emb = synth_embeddings(400, 64, seed=2, device="cuda").cpu()
+    np.random.seed(9)
+    want = oc.synthesize(emb, 0.1, 0.3, 100, 30, 3, 15, 6, q_start=10, return_debug=True)
+    if min(want["margins"]) > 1e-5:
+        assert res["q_ids"] == want["q_ids"] and res["jump_count"] == want["jump_count"]
