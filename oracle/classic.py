@@ -208,6 +208,17 @@ def threshold_margin(P3: torch.Tensor, thresholding: float, rows=None) -> float:
     return float(rel.min())
 
 
+# --------------------------------------------------------------------------- audio prior
+def compute_Paudio(t_audio_eg: torch.Tensor, driving_audio: torch.Tensor) -> torch.Tensor:
+    """computePaudio.py:6-18."""
+    import torch.nn.functional as F
+    s_a = F.normalize(t_audio_eg, dim=1)
+    d_a = F.normalize(driving_audio, dim=0).unsqueeze(0)
+    cos = torch.nn.CosineSimilarity(dim=1)
+    p_audio = cos(d_a.repeat([s_a.shape[0], 1]), s_a)
+    return p_audio / (p_audio.sum() + 1e-6)
+
+
 # --------------------------------------------------------------------------- walk
 def walk(P, model_type: int, fps: int, new_video_length: int, stride: int, filter_size: int,
          start: int = 100):

@@ -131,3 +131,16 @@ def test_cli_main_synthesis_mode(eng, capsys):
     want = oc.synthesize(emb, 0.1, 0.3, 100, 30, 3, 15, 6, q_start=10, return_debug=True)
     if min(want["margins"]) > 1e-5:
         assert res["q_ids"] == want["q_ids"] and res["jump_count"] == want["jump_count"]
+
+
+def test_compute_Paudio_dropin(eng):
+    """classic/computePaudio.py: the audio prior over T source examples."""
+    from audio_video_textures_b200.classic.computePaudio import compute_Paudio
+    from audio_video_textures_b200.synth import synth_audio_features
+    from oracle import classic as oc
+    t_a = synth_audio_features(300, 128, seed=4)
+    d = synth_audio_features(3, 128, seed=5)[1]
+    want = oc.compute_Paudio(t_a, d)
+    got = compute_Paudio(t_a.cuda(), d.cuda()).cpu()
+    np.testing.assert_allclose(got.numpy(), want.numpy(), rtol=1e-5, atol=1e-9)
+    np.testing.assert_allclose(float(got.sum()), 1.0, rtol=1e-5)

@@ -129,3 +129,22 @@ def test_contrastive_audio_conditioned():
                                da_driving=dad)
     np.testing.assert_array_equal(r["q_ids"], g["synth2_q_ids"])
     np.testing.assert_array_equal(r["frame_ids"], g["synth2_frame_ids"])
+
+
+def test_compute_Paudio_matches_reference_module():
+    """oracle.compute_Paudio against the unmodified reference module when /root/reference is present
+    (build container); elsewhere against its defining property."""
+    import os, sys
+    from audio_video_textures_b200.synth import synth_audio_features
+    t_a = synth_audio_features(50, 32, seed=1)
+    d = synth_audio_features(2, 32, seed=2)[0]
+    mine = classic.compute_Paudio(t_a, d)
+    ref_dir = "/root/reference/baselines/classic_video_textures"
+    if os.path.isdir(ref_dir):
+        sys.path.insert(0, ref_dir)
+        try:
+            from computePaudio import compute_Paudio as ref_fn
+            assert torch.equal(ref_fn(t_a, d), mine)
+        finally:
+            sys.path.remove(ref_dir)
+    np.testing.assert_allclose(float(mine.sum()), 1.0, rtol=1e-5)
