@@ -31,6 +31,23 @@ def test_cabi_library_exports_every_declared_symbol():
     assert isinstance(ctypes.CDLL(_lib.LIB_PATH), ctypes.CDLL)
 
 
+def test_ctypes_signatures_match_header_prototypes():
+    """Every prototype in include/avtex.h has as many parameters as the ctypes binding declares (ABI drift)."""
+    from audio_video_textures_b200 import _lib
+    text = open(os.path.join(ROOT, "include", "avtex.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    protos = re.findall(r"AVTEX_API\s+[\w\s\*]+?\b(avtex_\w+)\s*\(([^;]*?)\)\s*;", text, flags=re.S)
+    assert len(protos) >= 25
+    for name, params in protos:
+        params = params.strip()
+        n_params = 0 if params in ("", "void") else len(params.split(","))
+        if name == "avtex_last_error":
+            assert n_params == 0
+            continue
+        assert name in _lib.SIGNATURES, name
+        assert len(_lib.SIGNATURES[name]) == n_params, (name, n_params, len(_lib.SIGNATURES[name]))
+
+
 def test_product_path_has_no_cpu_fallback():
     if torch.cuda.is_available():
         pytest.skip("GPU present")
