@@ -8,6 +8,8 @@
 // issues (R-1)*s + fs loads for R outputs instead of R*fs, and the taps are compile-time indexed
 // kernel parameters (constant-bank FFMA operands: no shared-memory or LDS traffic at all).  Within
 // a warp consecutive threads own consecutive diagonals, so every load is a coalesced row segment.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace {
@@ -21,7 +23,7 @@ struct TapsBig { float w[960]; };
 // the first version stalled on instruction fetch (ncu: stalled_no_instruction was the top reason).
 __device__ __noinline__ float pow_pos_call(float x, float p) { return pow_pos(x, p); }
 
-template <int FS, int S, int FR>
+template <int FS, int S, int FR, bool PACKED>
 __global__ void __launch_bounds__(FT)
 diag_filter_kernel(const float *__restrict__ D1, int64_t ld1, int64_t in_row0, int64_t in_rows, const Taps64 taps,
                    int64_t a0, int64_t rows_out, int64_t m, float *__restrict__ D2, int64_t ld2,
@@ -44,7 +46,32 @@ diag_filter_kernel(const float *__restrict__ D1, int64_t ld1, int64_t in_row0, i
     // those on the matrix border)
     const bool interior = (b_blk * S >= 0) && ((b_blk + FT - 1) * S + T - 1 < n_in) &&
                           (grow + T - 1 < in_row0 + in_rows) && (grow + T - 1 < n_in);
-    if (interior) {
+    if (interior && PACKED) {
+        // Packed fp32x2 FMA (Blackwell FFMA2): outputs 2p and 2p+1 share one instruction.  At step t they
+        // need taps q = t - 2p and q - 1, so the pair (w[q], w[q-1]) is kept as one 64-bit register value
+        // (zero outside [0, FS)).  Same operation order per output as the scalar path -> identical bits,
+        // half the FMA issue slots (this kernel is issue-bound at stride 1: 40 FMAs + pow per output).
+        float2 wp[FS + 1];
+#pragma unroll
+        for (int q = 0; q <= FS; ++q)
+            wp[q] = make_float2(q < FS ? taps.w[q] : 0.f, q >= 1 ? taps.w[q - 1] : 0.f);
+        float2 acc2[FR / 2];
+#pragma unroll
+        for (int p2 = 0; p2 < FR / 2; ++p2) acc2[p2] = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int t = 0; t < T; ++t) {
+            const float x = __ldg(src);
+            src += step;
+            const float2 x2 = make_float2(x, x);
+#pragma unroll
+            for (int p2 = 0; p2 < FR / 2; ++p2) {
+                const int q = t - 2 * p2;
+                if (q >= 0 && q <= FS) acc2[p2] = __ffma2_rn(wp[q], x2, acc2[p2]);
+            }
+        }
+#pragma unroll
+        for (int p2 = 0; p2 < FR / 2; ++p2) { acc[2 * p2] = acc2[p2].x; acc[2 * p2 + 1] = acc2[p2].y; }
+    } else if (interior) {
 #pragma unroll
         for (int t = 0; t < T; ++t) {
             const float x = __ldg(src);
@@ -128,7 +155,12 @@ void launch_fast(const float *D1, int64_t ld1, int64_t in_row0, int64_t in_rows,
     for (int i = 0; i < 64; ++i) taps.w[i] = (i < FS) ? h_w[i] : 0.f;
     constexpr int FR = filter_r<S>();
     dim3 grid((unsigned)((m + FR - 1 + FT - 1) / FT), (unsigned)((rows_out + FR - 1) / FR));
-    diag_filter_kernel<FS, S, FR><<<grid, FT, 0, st>>>(D1, ld1, in_row0, in_rows, taps, a0, rows_out, m, D2, ld2, D3,
+    static const bool packed_off = []() { const char *e = getenv("AVTEX_FILTER_FFMA2"); return e != nullptr && e[0] == '0'; }();
+    if (S == 1 && !packed_off)
+        diag_filter_kernel<FS, S, FR, S == 1><<<grid, FT, 0, st>>>(D1, ld1, in_row0, in_rows, taps, a0, rows_out, m, D2, ld2, D3,
+                                                           ld3, p, sum, nnz);
+    else
+    diag_filter_kernel<FS, S, FR, false><<<grid, FT, 0, st>>>(D1, ld1, in_row0, in_rows, taps, a0, rows_out, m, D2, ld2, D3,
                                                    ld3, p, sum, nnz);
 }
 
