@@ -2,23 +2,28 @@
 //
 //   D[r,c] = sqrt( n_r + n_c - 2 <x_r, x_c> )        replaces classic/computeD1.py:50-56, 58-96
 //
-// x are the centred signed-byte frames written by K0 (pack.cu), n their exact squared norms.
-// tcgen05.mma kind::i8 (s8 x s8 -> s32 accumulated in TMEM) makes <x_r, x_c> an exact integer, so
-// d^2 is exact: no cancellation error, duplicate frames give exactly 0 (the reference's sigma
-// counts `nonzero(D1)`), and the only rounding left is one fp32 sqrt.  d^2 is evaluated modulo 2^32
-// in the epilogue, which is exact whenever the true d^2 < 2^32; the host wrapper guarantees that
-// through (sqrt(n_r)+sqrt(n_c))^2 <= 4 max(n) < 2^32 and otherwise routes to direct.cu.
+// x are byte frames: either the raw uint8 rows (unsigned operands, K0 = frame_norms_u8) or the centred
+// int8 copy written by pack.cu (signed operands); n are their exact sums of squares.  tcgen05.mma kind::i8
+// accumulates <x_r, x_c> in TMEM as int32 (modulo 2^32 for the unsigned form), the epilogue evaluates
+// n_r + n_c - 2g modulo 2^32, and the result is the EXACT integer d^2 whenever the true d^2 < 2^32: no
+// cancellation error, duplicate frames give exactly 0 (the reference's sigma counts `nonzero(D1)`), and the
+// only rounding left is one fp32 sqrt.  The host guarantees the domain through
+// d <= ||x_r - 128|| + ||x_c - 128||, i.e. 4 * max centred norm < 2^32, and otherwise routes to direct.cu.
 //
-// Structure (one persistent CTA per SM, 6 warps, warp-specialised):
-//   warp 0      TMA producer: cp.async.bulk.tensor 128B-swizzled tiles A[128 x 128B], B[256 x 128B]
-//               into a 4-stage shared-memory ring, completion on mbarriers.
-//   warp 1      MMA issuer (one lane): 4 x tcgen05.mma (M128 N256 K32) per stage, accumulators
-//               double-buffered in TMEM (2 x 256 columns); tcgen05.commit releases stages / signals
-//               the epilogue.
-//   warps 2-5   epilogue: tcgen05.ld 32 lanes x 32 columns at a time, fused  n_r + n_c - 2g -> sqrt,
-//               direct + mirrored stores, fused fp64 sum / non-zero count for sigma.
-//   Tiles are visited in groups of 16 row-tiles (8 for the 2-CTA kernel) so one wave's operand footprint stays inside L2;
-//   in symmetric mode only tiles touching the upper triangle are computed (~half the MMAs).
+// Work is a JOB LIST (GramJob: a rectangle of the matrix with a direct and/or a transposed destination, the
+// latter possibly in PEER memory); the tiles of all jobs are enumerated in L2-sized groups.  Two kernels:
+//   gram_l2_s8_2cta_kernel (default)  cluster of 2 CTAs, tcgen05.mma.cta_group::2, 256 x 256 tile:
+//       warp 0 (both CTAs)   TMA producer: its 128 A rows + its 128 of the 256 B rows per 128-byte K block into a
+//                            6-stage ring; completion bytes are credited to the leader's mbarrier
+//       warp 1 (leader)      one lane issues 4 MMAs (M256 N256 K32) per stage; multicast tcgen05.commit frees
+//                            the stage in both CTAs and signals both epilogues; accumulators double-buffered
+//                            in TMEM (2 x 256 columns) so the epilogue of tile i overlaps the MMAs of tile i+1
+//       warps 2-5 (both)     epilogue: tcgen05.ld 32 lanes x 32 columns, fused norm + sqrt, 32 x 32 transpose
+//                            through shared memory so every global store writes one full 128 B line (direct
+//                            rows and transposed rows), fp32/int partial sigma statistics per chunk
+//   gram_l2_s8_kernel (AVTEX_GRAM_MODE=1cta)  one CTA per SM, 128 x 256 tile, 4-stage 48 KB ring; kept as the
+//       measured baseline of the 2-CTA design (shared-memory bandwidth bound: 57.6 % vs 68 % tensor pipe).
+// Every mbarrier wait is bounded (trap, never hang).  DESIGN.md §4.1 has the measurements.
 #include <cuda.h>
 #include <stdlib.h>
 
