@@ -10,7 +10,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libavtex.so")
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 _p = C.c_void_p
 _i64 = C.c_int64
@@ -33,7 +33,9 @@ SIGNATURES = {
     "avtex_diag_filter_pow": [_p, _i64, _i64, _i64, C.POINTER(_f32), _int, _int, _i64, _i64, _i64,
                               _p, _i64, _p, _i64, _f32, _p, _p, _int, _p],
     "avtex_future_cost_sweep": [_p, _i64, _i64, _i64, _i64, _p, _p, _f32, _p, _p, _int, _p],
-    "avtex_future_cost_fused": [_p, _i64, _i64, _f32, _f32, _int, _p, _i64, _p, _p, _int, _p],
+    "avtex_future_cost_fused": [_p, _i64, _i64, _f32, _f32, _int, _p, _i64, _p, _p, _p, _int, _p],
+    "avtex_pow_matrix": [_p, _i64, _i64, _i64, _f32, _p, _i64, _int, _p],
+    "avtex_frame_norms_u8_push": [_p, _i64, _i64, _i64, _i64, C.POINTER(_p), C.POINTER(_p), _int, _int, _p],
     "avtex_future_cost_finalize": [_p, _i64, _i64, _i64, _i64, _p, _f32, _p, _i64, _p, _p, _int, _p],
     "avtex_transition_probs": [_p, _i64, _i64, _i64, _f32, _int, _i64, _p, _i64, _f32, _p, _i64, _p, _int, _p],
     "avtex_row_nnz": [_p, _i64, _i64, _i64, _p, _int, _p],
@@ -42,6 +44,8 @@ SIGNATURES = {
     "avtex_cosine_scores": [_p, _i64, _i64, _i64, _p, _f32, _p, _int, _p],
     "avtex_select_step": [_p, _p, _i64, _i64, _f32, _f32, _f32, _p, _p, _p, _int, _p],
     "avtex_audio_start": [_p, _i64, _i64, _i64, _p, _p, _p, _int, _p],
+    "avtex_synthesis_step": [_p, _i64, _i64, _i64, _p, _p, _i64, _i64, _p, _f32, _i64, _f32, _f32, _f32, _p, _p, _p,
+                             _p, _int, _p, _p, _p, _p, _int, _int, _int, _p],
     "avtex_gram_tile_schedule": [_int, _int, _int, C.POINTER(_int), C.POINTER(_int), _int],
     "avtex_gram_tile_schedule2": [_int, _int, _int, C.POINTER(_int), C.POINTER(_int), _int],
 }
@@ -56,8 +60,8 @@ class GramJob(C.Structure):
 
 SIGNATURES["avtex_future_cost_fused_peer"] = [_p, _i64, _i64, _i64, _i64, _f32, _f32, _int, _int, _int,
                                               C.POINTER(_p), _i64, C.POINTER(_p), C.POINTER(_p), C.c_uint,
-                                              _p, _p, _p, _int, _p]
-SIGNATURES["avtex_gram_l2_jobs"] = [_p, _int, _i64, _i64, _i64, _p, C.POINTER(GramJob), _int, _p, _p, _int, _p]
+                                              _p, _p, _p, _p, _int, _int, _p]
+SIGNATURES["avtex_gram_l2_jobs"] = [_p, _int, _i64, _i64, _i64, _p, C.POINTER(GramJob), _int, _p, _p, _p, _int, _p]
 
 _lib = None
 

@@ -25,8 +25,7 @@ def q_learning(
         D2 = D2.cuda()
     if D2.stride(-1) != 1:
         D2 = D2.contiguous()
-    # D3 = D2 ** p through the filter kernel's fused pow with the identity tap (fs = 1, stride 1)
-    _, D3 = engine.diag_filter(D2, 1, 1, p=p, taps=[1.0])
+    D3 = engine.pow_matrix(D2, p)                                      # q_learning.py:34
     fc = engine.future_cost_fused(D3, alpha, verbose=True)
     stats = engine.new_stats(D2.device)
     D3_new = engine.future_cost_finalize(D3, fc.mvec, alpha, stats=stats)

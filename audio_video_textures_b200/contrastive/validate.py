@@ -6,8 +6,9 @@ Per step the reference re-encodes ALL L target windows through a 3D CNN on every
     K6  o = <q^, T^> / temp            streaming GEMV, 4 L D bytes
     K6  a = <d^_step, S^> / temp       (audio-conditioned only)
     K7  o/sum, a/sum, alpha-mix, threshold at max - th*max, renormalise, ordered survivor list
-followed by one small D2H copy; the uniform draw stays `np.random.choice` on the host so the chosen
-sequence is bit-identical to the reference under the same seed.
+all inside ONE cooperative launch (avtex_synthesis_step) that writes the survivor list into mapped pinned
+memory; the uniform draw stays `np.random.choice` on the host so the chosen sequence is bit-identical to the
+reference under the same seed.
 `mini_batchsize` (-mbs) only shapes the reference's DataParallel chunks (validate.py:409-411,
 utils.py:208-260); at the embedding boundary the result layout is contiguous, so it is accepted
 and ignored.
@@ -57,28 +58,19 @@ class SynthesisState:
         if da_driving is not None:
             self.sn = engine.l2_normalize_rows(clamp_rows(da_source.float()))
             self.dn = engine.l2_normalize_rows(da_driving.float())
-        self.o = torch.empty(L, dtype=torch.float32, device=dev)
-        self.a = torch.empty(L, dtype=torch.float32, device=dev) if da_driving is not None else None
-        self.sel = torch.zeros(L + 1, dtype=torch.int32, device=dev)        # [count | choices...]
-        self.host = torch.empty(L + 1, dtype=torch.int32).pin_memory()
+        self.ws = engine.SynthesisWorkspace(L, dev, HOST_CAP)
         self.vals = None
+        self.launches_per_step = 1
 
     def step(self, q_id: int, iter_count: int, temp, alpha, threshold, want_vals=False):
-        """Returns the survivor window ids (numpy int32) in the reference's target-list order."""
-        engine.cosine_scores(self.tn, self.qn[q_id], temp, out=self.o)
-        if self.a is not None:
-            engine.cosine_scores(self.sn, self.dn[iter_count], temp, out=self.a)
+        """Returns the survivor window ids (numpy int32) in the reference's target-list order.  ONE kernel launch
+        (scores + audio scores + mix + threshold + ordered survivor list); the list arrives in mapped pinned
+        memory, the host polls its sequence word."""
         if want_vals and self.vals is None:
-            self.vals = torch.zeros(self.L, dtype=torch.float32, device=self.o.device)
-        engine.select_step(self.o, self.a, q_id, alpha, threshold, self.sel[1:], self.sel[:1],
-                           self.vals if want_vals else None)
-        cap = min(self.L, HOST_CAP)
-        self.host[:cap + 1].copy_(self.sel[:cap + 1], non_blocking=True)
-        torch.cuda.current_stream().synchronize()
-        n = int(self.host[0])
-        if n > cap:
-            self.host[:n + 1].copy_(self.sel[:n + 1])
-        return self.host[1:n + 1].numpy()
+            self.vals = torch.zeros(self.L, dtype=torch.float32, device=self.tn.device)
+        return engine.synthesis_step(self.ws, self.tn, self.qn[q_id], q_id, temp, alpha, threshold,
+                                     self.sn, self.dn[iter_count] if self.dn is not None else None,
+                                     self.vals if want_vals else None)
 
 
 def synthesize(t_emb, temp=0.1, threshold=0.0, fps=30, new_video_length=30, window=20, stride=4,
@@ -93,6 +85,8 @@ def synthesize(t_emb, temp=0.1, threshold=0.0, fps=30, new_video_length=30, wind
         q_start = 10 if da_driving is None else start_segment(mv(da_source), mv(da_driving)[0])
     W, S = window, stride
     max_length = math.ceil(fps) * new_video_length
+    if da_driving is not None:                                      # validate.py:260-263: a short driving clip caps the output
+        max_length = min(max_length, np.ceil(fps) * np.floor(len(da_driving) * S + W))
     q_id, p_q_id, iter_count, n_frames, jump_count = q_start, -1, 1, 0, 0
     q_ids, frame_ids, nz_counts = [], [], []
     while n_frames < max_length and (max_steps is None or len(q_ids) < max_steps):

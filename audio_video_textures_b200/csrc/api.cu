@@ -2,6 +2,8 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <atomic>
+
 #include "common.cuh"
 
 static thread_local char g_err[512] = "";
@@ -19,20 +21,20 @@ extern "C" const char *avtex_last_error(void) { return g_err; }
 
 // cudaGetDeviceProperties costs milliseconds; the three attributes needed are cached per device.
 extern "C" int avtex_device_info(int device, int *sm_count, int *cc) {
-    static int cached_sms[64], cached_cc[64];
-    static bool have[64] = {false};
+    // packed (sms << 16 | cc) + 1 in one atomic word per device: a racing second query stores the same value
+    static std::atomic<int> cached[64];
     AVTEX_REQUIRE(device >= 0 && device < 64, "device_info: device index %d out of range", device);
-    if (!have[device]) {
+    int packed = cached[device].load(std::memory_order_acquire);
+    if (packed == 0) {
         int sms = 0, major = 0, minor = 0;
         AVTEX_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
         AVTEX_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device));
         AVTEX_CUDA(cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, device));
-        cached_sms[device] = sms;
-        cached_cc[device] = major * 10 + minor;
-        have[device] = true;
+        packed = ((sms << 16) | (major * 10 + minor)) + 1;
+        cached[device].store(packed, std::memory_order_release);
     }
-    if (sm_count) *sm_count = cached_sms[device];
-    if (cc) *cc = cached_cc[device];
+    if (sm_count) *sm_count = (packed - 1) >> 16;
+    if (cc) *cc = (packed - 1) & 0xffff;
     return 0;
 }
 

@@ -93,23 +93,29 @@ __device__ __forceinline__ float4 ld_stream_f4(const float *p) {
 // powf() costs ~150 instructions per element and made the filter kernel compute-bound.  Here
 // x = 2^e * m (m in [1,2)):  x^p = 2^(p*e) * 2^(p*log2 m).  p is split as p_hi + p_lo with p_hi on
 // 12 bits, so p_hi*e is exact; its integer part goes straight into the exponent field and only
-// small-magnitude terms (|.| < 2) reach exp2f, keeping the result within ~3 ulp of powf (the
-// reference's CPU powf and CUDA's differ by that much already).  Subnormals/inf/nan take powf.
+// small-magnitude terms (|.| < 2) reach ex2, keeping the result within ~3 ulp of powf (the
+// reference's CPU powf and CUDA's differ by that much already).  Zero, subnormals, negatives, inf and
+// nan take the out-of-line powf.  lg2.approx / ex2.approx are what log2f / exp2f evaluate for arguments
+// in these ranges (m in [1,2), t in (-0.6, 1.6)); calling them directly only drops the range fix-ups.
+static __device__ __noinline__ float pow_slow(float x, float p) { return x == 0.f ? 0.f : powf(x, p); }
+
 __device__ __forceinline__ float pow_pos(float x, float p) {
-    if (x == 0.f) return 0.f;
-    const int ix = __float_as_int(x);
-    const int ebits = (ix >> 23) & 0xff;
-    if (ix < 0 || ebits == 0 || ebits == 0xff) return powf(x, p);
-    const float e = (float)(ebits - 127);
-    const float m = __int_as_float((ix & 0x007fffff) | 0x3f800000);
-    const float p_hi = __int_as_float(__float_as_int(p) & 0xfffff000);
+    const unsigned ix = __float_as_uint(x);
+    const unsigned e9 = ix >> 23;                  // sign + exponent
+    if (e9 - 1u >= 254u) return pow_slow(x, p);    // zero / subnormal / inf / nan / negative
+    const float e = (float)((int)e9 - 127);
+    const float m = __uint_as_float((ix & 0x007fffffu) | 0x3f800000u);
+    const float p_hi = __uint_as_float(__float_as_uint(p) & 0xfffff000u);
     const float p_lo = p - p_hi;
     const float a = p_hi * e;                      // exact: 12 x 8 bits
     const float ai = rintf(a);
-    if (fabsf(ai) > 100.f) return powf(x, p);      // result exponent near the fp32 limits
+    if (fabsf(ai) > 100.f) return pow_slow(x, p);  // result exponent near the fp32 limits
     float t = a - ai;                              // exact, |t| <= 0.5
     t = fmaf(p_lo, e, t);
-    t = fmaf(p, log2f(m), t);                      // in (-0.6, 1.6)
-    const float r = exp2f(t);                      // in (0.65, 3.1)
+    float lg;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg) : "f"(m));
+    t = fmaf(p, lg, t);                            // in (-0.6, 1.6)
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(t));   // in (0.65, 3.1)
     return __int_as_float(__float_as_int(r) + ((int)ai << 23));
 }

@@ -155,7 +155,7 @@ future_cost_finalize_kernel(const float *__restrict__ D3, int64_t ld, int64_t ro
 // eps it replaces cost ~25 us each.
 __global__ void __launch_bounds__(ST)
 future_cost_fused_kernel(const float *__restrict__ D3, int64_t ld, int64_t m, float alpha, float eps_stop,
-                         int max_sweeps, float *mbuf, int64_t mpad, double *eps_trail, int *info) {
+                         int max_sweeps, float *mbuf, int64_t mpad, double *eps_trail, int *info, float *m_out) {
     __shared__ float fred[32];
     __shared__ double dred[32];
     cg::grid_group grid = cg::this_grid();
@@ -190,6 +190,11 @@ future_cost_fused_kernel(const float *__restrict__ D3, int64_t ld, int64_t m, fl
         const float eps = (float)(num / ((double)m * (double)m));
         if (!(eps > eps_stop)) {
             if (blockIdx.x == 0 && threadIdx.x == 0) { info[0] = p; info[1] = cur; }
+            // the converged vector goes to a fixed place, so the host can launch the finalize kernel
+            // without first reading which of the three rotating buffers holds it
+            if (m_out != nullptr)
+                for (int64_t k = int64_t(blockIdx.x) * ST + threadIdx.x; k < m; k += int64_t(gridDim.x) * ST)
+                    m_out[k] = __ldcg(buf[cur] + k);
             return;
         }
         prev2 = cur;
@@ -218,33 +223,38 @@ struct FcPeerArgs {
     unsigned int *flags[8];      // rank r's `world` counters
     double *eps_local;           // [max_sweeps + 1], zeroed: this rank's numerators (atomicAdd target)
     double *eps_trail;           // [max_sweeps + 1] out: summed numerators
-    int *info;
+    int *info;                   // [0] sweeps (0: not converged)  [1] buffer index  [2] error (1: peer timeout)
+    float *m_out;                // nullable [mpad]: the converged vector (local)
+    long long timeout_cycles;
 };
 
-__device__ __forceinline__ void fc_peer_exchange(cg::grid_group &grid, const FcPeerArgs &a, int step, bool with_eps) {
+// Closes one sweep across the GPUs: thread r of CTA 0 handles peer r (eps slot, flag, spin), so the
+// NVLink round trips to the peers overlap instead of queueing behind each other.  A peer that does
+// not show up within the bound makes every CTA of this rank leave the kernel with info[2] = 1 — no
+// __trap(), which would poison the CUDA context; the peers then time out the same way.
+__device__ __forceinline__ bool fc_peer_exchange(cg::grid_group &grid, const FcPeerArgs &a, int step, bool with_eps) {
     grid.sync();                                     // all local rows done, all pushes issued
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
+    if (blockIdx.x == 0 && threadIdx.x < a.world) {
+        const int r = threadIdx.x;
         const unsigned int target = a.epoch_base + (unsigned int)step + 1u;
-        __threadfence_system();                      // cumulative: orders every CTA's pushes before the flags
+        __threadfence_system();                      // cumulative: orders every CTA's pushes before the flag
         if (with_eps) {
             const double mine = *reinterpret_cast<volatile double *>(a.eps_local + step);
-            for (int r = 0; r < a.world; ++r)
-                *reinterpret_cast<volatile double *>(a.epsbuf[r] + (int64_t)step * a.world + a.rank) = mine;
+            *reinterpret_cast<volatile double *>(a.epsbuf[r] + (int64_t)step * a.world + a.rank) = mine;
             __threadfence_system();
         }
-        for (int r = 0; r < a.world; ++r) *reinterpret_cast<volatile unsigned int *>(a.flags[r] + a.rank) = target;
+        *reinterpret_cast<volatile unsigned int *>(a.flags[r] + a.rank) = target;
         const long long t0 = clock64();
-        for (int r = 0; r < a.world; ++r) {
-            while ((int)(*reinterpret_cast<volatile unsigned int *>(a.flags[a.rank] + r) - target) < 0) {
-                if (clock64() - t0 > 8000000000LL) {
-                    printf("avtex future_cost_fused_peer: rank %d timed out waiting for rank %d at step %d\n", a.rank, r, step);
-                    __trap();
-                }
+        while ((int)(*reinterpret_cast<volatile unsigned int *>(a.flags[a.rank] + r) - target) < 0) {
+            if (clock64() - t0 > a.timeout_cycles) {
+                atomicExch(a.info + 2, 1);
+                break;
             }
         }
         __threadfence_system();
     }
     grid.sync();                                     // the gathered vector / eps slots may now be read
+    return *reinterpret_cast<volatile int *>(a.info + 2) == 0;
 }
 
 __global__ void __launch_bounds__(ST)
@@ -263,7 +273,7 @@ future_cost_fused_peer_kernel(const FcPeerArgs a) {
         const float mn = block_reduce(acc.mn, INFINITY, OpMin(), fred);
         if (threadIdx.x == 0) push(0, j, mn);
     }
-    fc_peer_exchange(grid, a, 0, false);
+    if (!fc_peer_exchange(grid, a, 0, false)) return;
     int cur = 0, prev2 = -1;
     for (int p = 1; p <= a.max_sweeps; ++p) {
         const int out = 3 - cur - (prev2 < 0 ? (cur == 0 ? 1 : 0) : prev2);
@@ -281,7 +291,7 @@ future_cost_fused_peer_kernel(const FcPeerArgs a) {
             e_blk += block_reduce(acc.e, 0.0, OpAdd<double>(), dred);
         }
         if (threadIdx.x == 0 && e_blk != 0.0) atomicAdd(a.eps_local + p, e_blk);
-        fc_peer_exchange(grid, a, p, true);
+        if (!fc_peer_exchange(grid, a, p, true)) return;
         double num = 0.0;
         for (int r = 0; r < a.world; ++r)
             num += *reinterpret_cast<volatile double *>(a.epsbuf[a.rank] + (int64_t)p * a.world + r);
@@ -289,6 +299,9 @@ future_cost_fused_peer_kernel(const FcPeerArgs a) {
         const float eps = (float)(num / ((double)a.m * (double)a.m));
         if (!(eps > a.eps_stop)) {
             if (blockIdx.x == 0 && threadIdx.x == 0) { a.info[0] = p; a.info[1] = cur; }
+            if (a.m_out != nullptr)
+                for (int64_t k = int64_t(blockIdx.x) * ST + threadIdx.x; k < a.m; k += int64_t(gridDim.x) * ST)
+                    a.m_out[k] = __ldcg(mp + k);
             return;
         }
         prev2 = cur;
@@ -334,7 +347,7 @@ extern "C" int avtex_future_cost_finalize(const float *D3, int64_t ld, int64_t r
 
 extern "C" int avtex_future_cost_fused(const float *D3, int64_t ld, int64_t m, float alpha, float eps_stop,
                                        int max_sweeps, float *mbuf, int64_t mpad, double *eps_trail, int *info,
-                                       int device, void *stream) {
+                                       float *m_out, int device, void *stream) {
     AVTEX_ENTER(device);
     AVTEX_REQUIRE(m >= 2 && ld >= m && mpad >= m && mpad % 4 == 0 && max_sweeps >= 1,
                   "future_cost_fused: bad shape m=%lld ld=%lld mpad=%lld", (long long)m, (long long)ld, (long long)mpad);
@@ -348,7 +361,7 @@ extern "C" int avtex_future_cost_fused(const float *D3, int64_t ld, int64_t m, f
     int64_t grid = (int64_t)sms * per_sm;              // full occupancy: the sweeps are HBM/L2 streaming
     if (grid > m) grid = m;
     void *args[] = {(void *)&D3, (void *)&ld, (void *)&m, (void *)&alpha, (void *)&eps_stop, (void *)&max_sweeps,
-                    (void *)&mbuf, (void *)&mpad, (void *)&eps_trail, (void *)&info};
+                    (void *)&mbuf, (void *)&mpad, (void *)&eps_trail, (void *)&info, (void *)&m_out};
     AVTEX_CUDA(cudaLaunchCooperativeKernel((void *)future_cost_fused_kernel, dim3((unsigned)grid), dim3(ST), args, 0,
                                            as_stream(stream)));
     return 0;
@@ -358,8 +371,8 @@ extern "C" int avtex_future_cost_fused_peer(const float *D3, int64_t ld, int64_t
                                             float alpha, float eps_stop, int max_sweeps, int rank, int world,
                                             float *const *h_mbuf, int64_t mpad, double *const *h_epsbuf,
                                             unsigned int *const *h_flags, unsigned int epoch_base,
-                                            double *eps_local, double *eps_trail, int *info, int device,
-                                            void *stream) {
+                                            double *eps_local, double *eps_trail, int *info, float *m_out,
+                                            int max_ctas, int device, void *stream) {
     AVTEX_ENTER(device);
     AVTEX_REQUIRE(world >= 1 && world <= 8 && rank >= 0 && rank < world, "future_cost_fused_peer: bad rank %d / world %d", rank, world);
     AVTEX_REQUIRE(m >= 2 && rows >= 1 && row0 >= 0 && row0 + rows <= m && ld >= m && mpad >= m && mpad % 4 == 0 &&
@@ -374,7 +387,8 @@ extern "C" int avtex_future_cost_fused_peer(const float *D3, int64_t ld, int64_t
         a.epsbuf[r] = r < world ? h_epsbuf[r] : nullptr;
         a.flags[r] = r < world ? h_flags[r] : nullptr;
     }
-    a.eps_local = eps_local; a.eps_trail = eps_trail; a.info = info;
+    a.eps_local = eps_local; a.eps_trail = eps_trail; a.info = info; a.m_out = m_out;
+    a.timeout_cycles = 20000000000LL;            // ~10 s: host-side skew is absorbed by the caller's barrier
     int sms = 0, cc = 0, per_sm = 0, coop = 0;
     if (int rc = avtex_device_info(device, &sms, &cc)) return rc;
     AVTEX_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device));
@@ -382,6 +396,10 @@ extern "C" int avtex_future_cost_fused_peer(const float *D3, int64_t ld, int64_t
     AVTEX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, future_cost_fused_peer_kernel, ST, 0));
     AVTEX_REQUIRE(per_sm >= 1, "future_cost_fused_peer: kernel does not fit on an SM");
     int64_t grid = (int64_t)sms * per_sm;
+    // max_ctas > 0: several ranks share ONE device ("virtual ranks", tests): their cooperative kernels must
+    // all be resident at the same time or the flag barrier would never close
+    if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
+    if (max_ctas < 0) grid = grid / (-max_ctas) > 0 ? grid / (-max_ctas) : 1;      // -G: an equal share for each of G ranks
     if (grid > rows) grid = rows;
     void *args[] = {(void *)&a};
     AVTEX_CUDA(cudaLaunchCooperativeKernel((void *)future_cost_fused_peer_kernel, dim3((unsigned)grid), dim3(ST), args, 0,

@@ -27,6 +27,8 @@
 #include <cuda.h>
 #include <stdlib.h>
 
+#include <atomic>
+
 #include "common.cuh"
 
 namespace {
@@ -77,6 +79,7 @@ struct GramArgs {
     unsigned long long *nnz;
     uint32_t idesc;                     // kind::i8 instruction descriptor (signed or unsigned operands)
     int num_jobs, num_tiles;
+    unsigned long long *clock_probe;    // nullable: [0] SM cycles, [1] ns spent by CTA 0's first epilogue warp
     GramJob jobs[MAX_JOBS];
 };
 
@@ -639,6 +642,12 @@ gram_l2_s8_2cta_kernel(const __grid_constant__ CUtensorMap map, const GramArgs a
         int acc = 0;
         uint32_t acc_phase = 0;
         EpiStats st{0.0, 0ull};
+        // in-kernel clock probe: SM cycles and wall nanoseconds over this CTA's whole tile loop give the
+        // SM clock the kernel actually ran at (NVML's 10 ms samples cannot see a 1 ms kernel)
+        const bool probe = (args.clock_probe != nullptr) && blockIdx.x == 0 && warp == 2 && lane == 0;
+        long long c0 = 0;
+        unsigned long long g0 = 0;
+        if (probe) { c0 = clock64(); asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g0)); }
         for (int t = cluster_id; t < args.num_tiles; t += num_clusters) {
             int tm, tn, lt;
             const GramJob &job = args.jobs[find_job(args, t, &lt)];
@@ -651,6 +660,12 @@ gram_l2_s8_2cta_kernel(const __grid_constant__ CUtensorMap map, const GramArgs a
                           job.col0 + int64_t(tn) * BN, lane, epi_tile,
                           [release]() { mbar_arrive_cluster(release, 0); }, st);
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+        if (probe) {
+            unsigned long long g1;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g1));
+            args.clock_probe[0] = (unsigned long long)(clock64() - c0);
+            args.clock_probe[1] = g1 - g0;
         }
         epilogue_flush(args, st, lane);
     }
@@ -666,16 +681,16 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t
                                   CUtensorMapFloatOOBfill);
 
 int get_encode_fn(EncodeTiledFn *out) {
-    static EncodeTiledFn cached = nullptr;
-    if (cached == nullptr) {
+    static std::atomic<EncodeTiledFn> cached{nullptr};      // idempotent: a racing second lookup stores the same pointer
+    if (cached.load(std::memory_order_acquire) == nullptr) {
         void *fn = nullptr;
         cudaDriverEntryPointQueryResult qres;
         AVTEX_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
         AVTEX_REQUIRE(fn != nullptr && qres == cudaDriverEntryPointSuccess,
                       "cuTensorMapEncodeTiled not available from the driver");
-        cached = reinterpret_cast<EncodeTiledFn>(fn);
+        cached.store(reinterpret_cast<EncodeTiledFn>(fn), std::memory_order_release);
     }
-    *out = cached;
+    *out = cached.load(std::memory_order_acquire);
     return 0;
 }
 
@@ -694,7 +709,7 @@ int make_map(EncodeTiledFn enc, CUtensorMap *map, const void *base, int64_t n, i
 
 int launch_gram_jobs(const void *operand, bool is_signed, int64_t n, int64_t k_extent, int64_t pitch,
                      const int64_t *sqnorm, const AvtexGramJob *jobs, int num_jobs, double *sum,
-                     unsigned long long *nnz, int device, void *stream) {
+                     unsigned long long *nnz, unsigned long long *clock_probe, int device, void *stream) {
     AVTEX_ENTER(device);
     AVTEX_REQUIRE(n >= 1 && n < (int64_t(1) << 30) && k_extent >= 1 && k_extent < (int64_t(1) << 31),
                   "gram_l2: bad shape n=%lld k=%lld", (long long)n, (long long)k_extent);
@@ -713,6 +728,7 @@ int launch_gram_jobs(const void *operand, bool is_signed, int64_t n, int64_t k_e
     a.n = n; a.kp = k_extent; a.sqnorm = sqnorm; a.sum = sum; a.nnz = nnz;
     a.idesc = make_idesc(bm, is_signed);
     a.num_jobs = num_jobs;
+    a.clock_probe = clock_probe;
     int total = 0;
     for (int j = 0; j < num_jobs; ++j) {
         const AvtexGramJob &in = jobs[j];
@@ -746,10 +762,11 @@ int launch_gram_jobs(const void *operand, bool is_signed, int64_t n, int64_t k_e
     if (two_cta) {
         CUtensorMap map;
         if (int rc = make_map(enc, &map, operand, n, k_extent, pitch, BM)) return rc;
-        static bool attr2_set[64] = {false};
-        if (device < 64 && !attr2_set[device]) {
+        // cudaFuncSetAttribute is idempotent: the atomic flag only skips repeats, two racing host threads both succeed
+        static std::atomic<bool> attr2_set[64];
+        if (device >= 64 || !attr2_set[device].load(std::memory_order_acquire)) {
             AVTEX_CUDA(cudaFuncSetAttribute(gram_l2_s8_2cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES));
-            attr2_set[device] = true;
+            if (device < 64) attr2_set[device].store(true, std::memory_order_release);
         }
         int clusters = sms / 2;
         if (a.num_tiles < clusters) clusters = a.num_tiles;
@@ -760,10 +777,10 @@ int launch_gram_jobs(const void *operand, bool is_signed, int64_t n, int64_t k_e
     CUtensorMap map_a, map_b;
     if (int rc = make_map(enc, &map_a, operand, n, k_extent, pitch, BM)) return rc;
     if (int rc = make_map(enc, &map_b, operand, n, k_extent, pitch, BN)) return rc;
-    static bool attr_set[64] = {false};
-    if (device < 64 && !attr_set[device]) {
+    static std::atomic<bool> attr_set[64];
+    if (device >= 64 || !attr_set[device].load(std::memory_order_acquire)) {
         AVTEX_CUDA(cudaFuncSetAttribute(gram_l2_s8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-        attr_set[device] = true;
+        if (device < 64) attr_set[device].store(true, std::memory_order_release);
     }
     const int grid = a.num_tiles < sms ? a.num_tiles : sms;
     gram_l2_s8_kernel<<<grid, NUM_THREADS, SMEM_BYTES, as_stream(stream)>>>(map_a, map_b, a);
@@ -784,7 +801,7 @@ int launch_gram(const void *operand, bool is_signed, int64_t n, int64_t k_extent
     job.DT = symmetric ? D : nullptr; job.dt_row0 = 0; job.ldt = ldd;
     job.symmetric = symmetric ? 1 : 0;
     job.count_stats = 1;
-    return launch_gram_jobs(operand, is_signed, n, k_extent, pitch, sqnorm, &job, 1, sum, nnz, device, stream);
+    return launch_gram_jobs(operand, is_signed, n, k_extent, pitch, sqnorm, &job, 1, sum, nnz, nullptr, device, stream);
 }
 
 }  // namespace
@@ -803,8 +820,9 @@ extern "C" int avtex_gram_l2_u8(const uint8_t *frames, int64_t n, int64_t k, int
 
 extern "C" int avtex_gram_l2_jobs(const void *operand, int operand_signed, int64_t n, int64_t k, int64_t ld,
                                   const int64_t *sqnorm, const AvtexGramJob *h_jobs, int num_jobs, double *sum,
-                                  unsigned long long *nnz, int device, void *stream) {
-    return launch_gram_jobs(operand, operand_signed != 0, n, k, ld, sqnorm, h_jobs, num_jobs, sum, nnz, device, stream);
+                                  unsigned long long *nnz, unsigned long long *clock_probe, int device, void *stream) {
+    return launch_gram_jobs(operand, operand_signed != 0, n, k, ld, sqnorm, h_jobs, num_jobs, sum, nnz, clock_probe, device,
+                            stream);
 }
 
 extern "C" int avtex_gram_tile_schedule2(int TM, int TN, int symmetric, int *tm_out, int *tn_out, int capacity) {

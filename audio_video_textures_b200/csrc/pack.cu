@@ -95,24 +95,44 @@ pack_f32_kernel(const float *__restrict__ in, int64_t k, int64_t ld, int8_t *__r
 // Norms only (no packed copy): the Gram kernel can contract the raw unsigned bytes directly
 // (kind::i8 with unsigned operands, see gram.cu), which needs sum x^2 per frame for the epilogue and the
 // CENTRED norm sum (x-128)^2 = sum x^2 - 256 sum x + 128^2 k for the d^2 < 2^32 domain guard.
+// Results can be written to up to 8 destinations (the same vector on every GPU of the box, through
+// peer-mapped pointers): the row-sharded path computes 1/G of the norms per rank and PUSHES them to its
+// peers from this kernel instead of running an all-gather + all-reduce afterwards.
+struct NormDst {
+    int64_t *sqnorm[8];                 // base of the full [N] vector on destination d
+    unsigned long long *max_centred[8]; // nullable
+    int count;
+};
+
+__device__ __forceinline__ void norms_accum16(const uint4 v, unsigned long long &sq, unsigned long long &sm) {
+    unsigned int q = 0, t = 0;
+    q = __dp4a(v.x, v.x, q); q = __dp4a(v.y, v.y, q); q = __dp4a(v.z, v.z, q); q = __dp4a(v.w, v.w, q);
+    t = __dp4a(v.x, 0x01010101u, t); t = __dp4a(v.y, 0x01010101u, t);
+    t = __dp4a(v.z, 0x01010101u, t); t = __dp4a(v.w, 0x01010101u, t);
+    sq += q;
+    sm += t;
+}
+
+__device__ __forceinline__ void norms_store(const NormDst &dst, int64_t grow, int64_t k, unsigned long long sq,
+                                            unsigned long long sm) {
+    const unsigned long long centred = sq + 16384ull * (unsigned long long)k - 256ull * sm;
+    for (int d = 0; d < dst.count; ++d) {
+        dst.sqnorm[d][grow] = (int64_t)sq;
+        if (dst.max_centred[d] != nullptr) atomicMax(dst.max_centred[d], centred);
+    }
+}
+
+// long rows (>= 32 KB): one CTA per row
 __global__ void __launch_bounds__(PACK_THREADS)
-frame_norms_u8_kernel(const uint8_t *__restrict__ in, int64_t k, int64_t ld, int64_t *__restrict__ sqnorm,
-                      unsigned long long *__restrict__ max_centred) {
+frame_norms_u8_kernel(const uint8_t *__restrict__ in, int64_t k, int64_t ld, int64_t row0, const NormDst dst) {
     __shared__ unsigned long long scratch[32];
     const int64_t row = blockIdx.x;
     const uint8_t *src = in + row * ld;
     unsigned long long sq = 0, sm = 0;
     const bool vec = ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
     const int64_t kv = vec ? (k & ~int64_t(15)) : 0;
-    for (int64_t c = int64_t(threadIdx.x) * 16; c < kv; c += int64_t(PACK_THREADS) * 16) {
-        const uint4 v = __ldg(reinterpret_cast<const uint4 *>(src + c));
-        unsigned int q = 0, t = 0;
-        q = __dp4a(v.x, v.x, q); q = __dp4a(v.y, v.y, q); q = __dp4a(v.z, v.z, q); q = __dp4a(v.w, v.w, q);
-        t = __dp4a(v.x, 0x01010101u, t); t = __dp4a(v.y, 0x01010101u, t);
-        t = __dp4a(v.z, 0x01010101u, t); t = __dp4a(v.w, 0x01010101u, t);
-        sq += q;
-        sm += t;
-    }
+    for (int64_t c = int64_t(threadIdx.x) * 16; c < kv; c += int64_t(PACK_THREADS) * 16)
+        norms_accum16(__ldg(reinterpret_cast<const uint4 *>(src + c)), sq, sm);
     for (int64_t c = kv + threadIdx.x; c < k; c += PACK_THREADS) {
         const unsigned int v = src[c];
         sq += v * v;
@@ -120,10 +140,38 @@ frame_norms_u8_kernel(const uint8_t *__restrict__ in, int64_t k, int64_t ld, int
     }
     sq = block_reduce(sq, 0ull, OpAdd<unsigned long long>(), scratch);
     sm = block_reduce(sm, 0ull, OpAdd<unsigned long long>(), scratch);
-    if (threadIdx.x == 0) {
-        sqnorm[row] = (int64_t)sq;
-        if (max_centred != nullptr) atomicMax(max_centred, sq + 16384ull * (unsigned long long)k - 256ull * sm);
+    if (threadIdx.x == 0) norms_store(dst, row0 + row, k, sq, sm);
+}
+
+// short rows (a 64x64 RGB frame is 12 KB): one WARP per row, 8 rows per CTA, four 128-bit loads in flight per
+// lane.  One CTA per 12 KB row spent most of its life in launch / reduction overhead (0.67 of the HBM peak).
+__global__ void __launch_bounds__(PACK_THREADS)
+frame_norms_u8_warp_kernel(const uint8_t *__restrict__ in, int64_t n, int64_t k, int64_t ld, int64_t row0,
+                           const NormDst dst) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row = int64_t(blockIdx.x) * (PACK_THREADS / 32) + (threadIdx.x >> 5);
+    if (row >= n) return;
+    const uint8_t *src = in + row * ld;
+    unsigned long long sq = 0, sm = 0;
+    const bool vec = ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
+    const int64_t kv = vec ? (k & ~int64_t(15)) : 0;
+    int64_t c = int64_t(lane) * 16;
+    for (; c + 3 * 512 < kv; c += 4 * 512) {
+        const uint4 v0 = __ldg(reinterpret_cast<const uint4 *>(src + c)),
+                    v1 = __ldg(reinterpret_cast<const uint4 *>(src + c + 512)),
+                    v2 = __ldg(reinterpret_cast<const uint4 *>(src + c + 1024)),
+                    v3 = __ldg(reinterpret_cast<const uint4 *>(src + c + 1536));
+        norms_accum16(v0, sq, sm); norms_accum16(v1, sq, sm); norms_accum16(v2, sq, sm); norms_accum16(v3, sq, sm);
     }
+    for (; c < kv; c += 512) norms_accum16(__ldg(reinterpret_cast<const uint4 *>(src + c)), sq, sm);
+    for (int64_t t = kv + lane; t < k; t += 32) {
+        const unsigned int v = src[t];
+        sq += v * v;
+        sm += v;
+    }
+    sq = warp_sum(sq);
+    sm = warp_sum(sm);
+    if (lane == 0) norms_store(dst, row0 + row, k, sq, sm);
 }
 
 }  // namespace
@@ -158,12 +206,38 @@ extern "C" int avtex_pack_frames_f32(const float *frames, int64_t n, int64_t k, 
     return 0;
 }
 
-extern "C" int avtex_frame_norms_u8(const uint8_t *frames, int64_t n, int64_t k, int64_t ld, int64_t *sqnorm,
-                                    unsigned long long *max_centred, int device, void *stream) {
+static int launch_norms(const uint8_t *frames, int64_t n, int64_t k, int64_t ld, int64_t row0, const NormDst &dst,
+                        int device, void *stream) {
     AVTEX_ENTER(device);
-    AVTEX_REQUIRE(n > 0 && k > 0 && ld >= k && n < (int64_t(1) << 31), "frame_norms_u8: bad shape n=%lld k=%lld ld=%lld",
-                  (long long)n, (long long)k, (long long)ld);
-    frame_norms_u8_kernel<<<(unsigned)n, PACK_THREADS, 0, as_stream(stream)>>>(frames, k, ld, sqnorm, max_centred);
+    AVTEX_REQUIRE(n > 0 && k > 0 && ld >= k && n < (int64_t(1) << 31) && row0 >= 0,
+                  "frame_norms_u8: bad shape n=%lld k=%lld ld=%lld", (long long)n, (long long)k, (long long)ld);
+    if (k < 32768)
+        frame_norms_u8_warp_kernel<<<(unsigned)((n + PACK_THREADS / 32 - 1) / (PACK_THREADS / 32)), PACK_THREADS, 0,
+                                     as_stream(stream)>>>(frames, n, k, ld, row0, dst);
+    else
+        frame_norms_u8_kernel<<<(unsigned)n, PACK_THREADS, 0, as_stream(stream)>>>(frames, k, ld, row0, dst);
     AVTEX_LAUNCH_CHECK();
     return 0;
+}
+
+extern "C" int avtex_frame_norms_u8(const uint8_t *frames, int64_t n, int64_t k, int64_t ld, int64_t *sqnorm,
+                                    unsigned long long *max_centred, int device, void *stream) {
+    NormDst dst;
+    for (int d = 0; d < 8; ++d) { dst.sqnorm[d] = nullptr; dst.max_centred[d] = nullptr; }
+    dst.sqnorm[0] = sqnorm; dst.max_centred[0] = max_centred; dst.count = 1;
+    return launch_norms(frames, n, k, ld, 0, dst, device, stream);
+}
+
+extern "C" int avtex_frame_norms_u8_push(const uint8_t *frames, int64_t n, int64_t k, int64_t ld, int64_t row0,
+                                         int64_t *const *h_sqnorm, unsigned long long *const *h_max_centred,
+                                         int num_dst, int device, void *stream) {
+    AVTEX_REQUIRE(num_dst >= 1 && num_dst <= 8 && h_sqnorm != nullptr, "frame_norms_u8_push: 1..8 destinations (got %d)", num_dst);
+    NormDst dst;
+    for (int d = 0; d < 8; ++d) {
+        dst.sqnorm[d] = d < num_dst ? h_sqnorm[d] : nullptr;
+        dst.max_centred[d] = (d < num_dst && h_max_centred != nullptr) ? h_max_centred[d] : nullptr;
+        AVTEX_REQUIRE(d >= num_dst || dst.sqnorm[d] != nullptr, "frame_norms_u8_push: destination %d is NULL", d);
+    }
+    dst.count = num_dst;
+    return launch_norms(frames, n, k, ld, row0, dst, device, stream);
 }

@@ -5,6 +5,8 @@
 //   warp-shuffle + shared-memory block reductions.
 #include <float.h>
 
+#include <atomic>
+
 #include "common.cuh"
 
 namespace {
@@ -194,13 +196,13 @@ extern "C" int avtex_transition_probs(const float *D, int64_t ld, int64_t rows_i
     AVTEX_REQUIRE(sigma > 0.f, "transition_probs: sigma must be positive (got %g)", (double)sigma);
     if (cols <= PROBS_SMEM_COLS) {
         const size_t smem = (size_t)cols * sizeof(float);
-        static bool attr_set[64] = {false};
-        if (device >= 0 && device < 64 && !attr_set[device]) {
+        static std::atomic<bool> attr_set[64];       // the attribute calls are idempotent; the flag only skips repeats
+        if (device < 0 || device >= 64 || !attr_set[device].load(std::memory_order_acquire)) {
             AVTEX_CUDA(cudaFuncSetAttribute(transition_probs_kernel<true, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             PROBS_SMEM_COLS * (int)sizeof(float)));
             AVTEX_CUDA(cudaFuncSetAttribute(transition_probs_kernel<true, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             PROBS_SMEM_COLS * (int)sizeof(float)));
-            attr_set[device] = true;
+            if (device >= 0 && device < 64) attr_set[device].store(true, std::memory_order_release);
         }
         if (cols >= 8192)       // long rows: few CTAs fit per SM (shared memory), so make each one wide
             transition_probs_kernel<true, 1024><<<(unsigned)rows_out, 1024, smem, as_stream(stream)>>>(

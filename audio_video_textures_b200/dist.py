@@ -1,20 +1,35 @@
 """Row-sharded classic++ transition matrix over the GPUs of one box (one process per GPU).
 
 Rank r owns rows [a0, a1) of every M x M matrix (D2, D3, D3_new, P3) and the D1 rows those need
-(`a*stride + k`, plus one halo output row for the row shift of P, over-computed locally instead of
-exchanged: ~fs extra D1 rows out of N/G).  Frames are replicated (N*K bytes, 1.2 GB at N = 100k,
-64x64).  The ONLY data-path exchange is the one the algorithm has: after each future-cost sweep
-the per-row minima (M fp32) are all-gathered and the eps numerator (one fp64) is all-reduced
-(BASELINE.json north_star).  sigma needs one more all-reduce of (sum, nnz).
+(`a*stride + k`, plus one halo output row for the row shift of P).  Frames are replicated (N*K bytes,
+1.2 GB at N = 100k, 64x64).  The ONLY data-path exchange the algorithm has is the per-sweep all-gather of
+the row minima + the eps numerator (BASELINE.json north_star); it and the two exchanges
+the sharding adds (frame norms, transposed Gram tiles) are done by the kernels themselves through
+peer-mapped pointers:
+
+  * K0   every rank computes the norms of 1/G of the frames and PUSHES them into every peer's vector
+  * K1   symmetric Gram: each off-diagonal rectangle is split between the two ranks that need it; the tile
+         kernel stores it locally and pushes the transpose into the peer's shard (NVLink stores)
+  * K3   one cooperative kernel per GPU runs all sweeps; minima / eps are pushed to the peers, a flag
+         barrier closes each sweep
+
+`RankStep` holds one rank's phases; `classic_sharded` runs them for a real rank (torch symmetric memory,
+stream-ordered barriers between phases), `VirtualBox` runs G of them on ONE device (peer pointers = plain
+local buffers, ranks executed phase by phase) so that the 8-rank job lists, halo plans and the flag
+protocol are parity-tested on a single-GPU box.  The NCCL form of the same algorithm (`make_exchange`,
+`--no_symmetric`) remains as the fallback when symmetric memory is unavailable and as the gloo-testable
+host logic.
 """
 from __future__ import annotations
 
+import ctypes as C
 from dataclasses import dataclass
 
+import numpy as np
 import torch
 import torch.distributed as dist
 
-from . import engine
+from . import _lib, engine
 
 
 @dataclass(frozen=True)
@@ -47,6 +62,69 @@ def plan_shards(n: int, filter_size: int, stride: int, world: int, rank: int) ->
     return ShardPlan(n, m, world, rank, shard, a0, a1, a1h, a0 * stride, r_hi)
 
 
+def core_rows(plans: list, r: int, stride: int):
+    """Disjoint cover of the frame rows: the D1 rows rank r is responsible for computing."""
+    p = plans[r]
+    return p.a0 * stride, (p.n if r == p.world - 1 else p.a1 * stride)
+
+
+def pair_split(lo: int, hi: int) -> int:
+    """Column split point of core_j for the pair (i < j): rank i computes core_i x [lo, mid) and rank j
+    computes [mid, hi) x core_i, each pushing the transpose to the other, so both do half of the rectangle
+    whatever the number of ranks.  Aligned to the 256-wide tile."""
+    mid = lo + (hi - lo) // 2
+    mid = lo + (mid - lo + 255) // 256 * 256
+    return min(mid, hi)
+
+
+def symmetric_jobs(plans: list, me: int, ptrs: list, ld: int, stride: int) -> list:
+    """Gram job list of rank `me` (pure function of the plans and the shard base pointers): its own
+    symmetric diagonal block plus, per peer, its half of the off-diagonal rectangle with the transposed
+    destination in the PEER's shard.  Peers are visited in rotated order (me+1, me+2, ...): at any moment
+    every rank pushes into a DIFFERENT destination instead of all ranks hammering one GPU's NVLink ingress."""
+    world = len(plans)
+    p = plans[me]
+    lo, hi = core_rows(plans, me, stride)
+    mine = dict(D=ptrs[me], d_row0=p.r_lo, ldd=ld)
+    out = [dict(row0=lo, rows=hi - lo, col0=lo, cols=hi - lo, symmetric=1, count_stats=1,
+                DT=ptrs[me], dt_row0=p.r_lo, ldt=ld, **mine)]
+    for step in range(1, world):
+        other = (me + step) % world
+        olo, ohi = core_rows(plans, other, stride)
+        peer = dict(DT=ptrs[other], dt_row0=plans[other].r_lo, ldt=ld)
+        if me < other:                                  # my rows x the first half of the peer's columns
+            mid = pair_split(olo, ohi)
+            if mid > olo:
+                out.append(dict(row0=lo, rows=hi - lo, col0=olo, cols=mid - olo, symmetric=0, count_stats=1,
+                                **peer, **mine))
+        else:                                           # the second half of my rows x the peer's columns
+            mid = pair_split(lo, hi)
+            if hi > mid:
+                out.append(dict(row0=mid, rows=hi - mid, col0=olo, cols=ohi - olo, symmetric=0, count_stats=1,
+                                **peer, **mine))
+    return out
+
+
+def halo_sources(plans: list, me: int, stride: int) -> list:
+    """Rows past rank `me`'s core that its filter outputs read, as (owner rank, first row, rows) pieces taken
+    from the owners' CORE rows only.  When shard*stride < filter_size (small M over many ranks) the halo spans
+    several following ranks; reading a neighbour's own halo region instead would race with its halo copy."""
+    need_lo, need_hi = core_rows(plans, me, stride)[1], plans[me].r_hi
+    out = []
+    r = me + 1
+    while need_lo < need_hi:
+        if r >= len(plans):
+            raise ValueError("halo rows beyond the last rank's core")
+        clo, chi = core_rows(plans, r, stride)
+        take = min(need_hi, chi) - need_lo
+        if take > 0:
+            out.append((r, need_lo, take))
+            need_lo += take
+        r += 1
+    return out
+
+
+# --------------------------------------------------------------------------- NCCL form (fallback / gloo tests)
 def load_frames_sharded(host_frames: torch.Tensor, rank: int, world: int, device, group=None) -> torch.Tensor:
     """Replicates a HOST-resident uint8 clip on every GPU without sending it over every PCIe link: each
     rank copies only its 1/G slice host->device, then the slices are all-gathered over NVLink (in place).
@@ -64,8 +142,8 @@ def load_frames_sharded(host_frames: torch.Tensor, rank: int, world: int, device
 
 
 def pack_frames_sharded(frames: torch.Tensor, rank: int, world: int, group=None) -> engine.PackedFrames:
-    """K0 for the replicated clip: every rank computes the norms of 1/G of the frames and the [N] int64 vector is
-    all-gathered (113 KB at N = 14144) instead of every rank reading all N*K bytes again."""
+    """K0 for the replicated clip, NCCL form: every rank computes the norms of 1/G of the frames and the [N]
+    int64 vector is all-gathered.  (The symmetric-memory path pushes them from the kernel instead.)"""
     x = frames.reshape(frames.shape[0], -1)
     n, k = x.shape
     if world == 1 or x.dtype != torch.uint8 or x.stride(0) % 16 != 0 or x.data_ptr() % 16 != 0 or x.stride(1) != 1:
@@ -117,17 +195,56 @@ def allreduce_stats(stats: torch.Tensor, group=None) -> torch.Tensor:
     return out
 
 
-def pair_split(lo: int, hi: int) -> int:
-    """Column split point of core_j for the pair (i < j): rank i computes core_i x [lo, mid) and rank j
-    computes [mid, hi) x core_i, each pushing the transpose to the other, so both do half of the rectangle
-    whatever the number of ranks.  Aligned to the 256-wide tile."""
-    mid = lo + (hi - lo) // 2
-    mid = lo + (mid - lo + 255) // 256 * 256
-    return min(mid, hi)
+# --------------------------------------------------------------------------- peer-mapped workspaces
+class PeerBuffers:
+    """What one rank sees of the box: for every rank the base pointers of its D1 shard, norm vectors and
+    future-cost scratch, plus stream-ordered barriers.  Two providers: torch symmetric memory over NVLink
+    (`SymmetricShardWorkspace`) and plain local buffers shared by virtual ranks (`VirtualBox`)."""
+    MAX_SWEEPS = 2046
+
+    def __init__(self, n, filter_size, stride, rank, world, device):
+        self.n, self.fs, self.stride, self.rank, self.world, self.device = n, filter_size, stride, rank, world, device
+        self.plans = [plan_shards(n, filter_size, stride, world, r) for r in range(world)]
+        self.plan = self.plans[rank]
+        self.ld = (n + 31) // 32 * 32
+        self.rows_max = max(p.r_hi - p.r_lo for p in self.plans)
+        self.m = self.plan.m
+        self.mpad = (self.m + 31) // 32 * 32
+        self.npad = (n + 31) // 32 * 32
+        # byte layout of the small per-rank buffer: [2 x sqnorm int64 npad | 2 x flags int64[2] | 2 x 3 m-vectors |
+        # 2 x eps slots | sweep flags]
+        self.off_sq = 0
+        self.off_fl = self.off_sq + 2 * self.npad * 8
+        self.off_m = self.off_fl + 2 * 16
+        self.off_eps = self.off_m + 6 * self.mpad * 4
+        self.n_eps = (self.MAX_SWEEPS + 1) * world * 8
+        self.off_sweep = self.off_eps + 2 * self.n_eps
+        self.small_bytes = self.off_sweep + 256
+        self.calls = 0
+        # filled by the provider: d1 (local [rows_max, ld] fp32), small (local uint8), d1_ptrs / small_ptrs (ints)
+        self.d1 = self.small = None
+        self.d1_ptrs = self.small_ptrs = None
+
+    def barrier(self, channel: int):
+        raise NotImplementedError
+
+    def peer_d1_rows(self, r: int, row_off: int, rows: int) -> torch.Tensor:
+        raise NotImplementedError
+
+    # -- views into this rank's small buffer
+    def sqnorm(self, parity: int) -> torch.Tensor:
+        return self.small[self.off_sq + parity * self.npad * 8: self.off_sq + (parity + 1) * self.npad * 8].view(torch.int64)
+
+    def flags(self, parity: int) -> torch.Tensor:
+        return self.small[self.off_fl + parity * 16: self.off_fl + (parity + 1) * 16].view(torch.int64)
+
+    def D1(self) -> torch.Tensor:
+        p = self.plan
+        return self.d1[:p.r_hi - p.r_lo, :self.n]
 
 
-class SymmetricShardWorkspace:
-    """D1 row shards in torch symmetric memory (peer-mapped over NVLink / NVSwitch).
+class SymmetricShardWorkspace(PeerBuffers):
+    """Shards in torch symmetric memory (peer-mapped over NVLink / NVSwitch).
 
     Row sharding alone forfeits the factor-2 symmetry of the distance matrix: rank I needs D1[rows_I, :],
     and D1[rows_I, cols_J] is the transpose of D1[rows_J, cols_I] that rank J needs.  Here each off-diagonal
@@ -138,121 +255,138 @@ class SymmetricShardWorkspace:
 
     def __init__(self, n: int, filter_size: int, stride: int, rank: int, world: int, device, group=None):
         import torch.distributed._symmetric_memory as symm_mem
-        self.n, self.fs, self.stride, self.rank, self.world = n, filter_size, stride, rank, world
-        self.plans = [plan_shards(n, filter_size, stride, world, r) for r in range(world)]
-        self.plan = self.plans[rank]
-        self.ld = (n + 31) // 32 * 32
-        rows_max = max(p.r_hi - p.r_lo for p in self.plans)
+        super().__init__(n, filter_size, stride, rank, world, device)
         group = dist.group.WORLD if group is None else group
-        self.buf = symm_mem.empty((rows_max, self.ld), dtype=torch.float32, device=device)
-        self.hdl = symm_mem.rendezvous(self.buf, group.group_name)
-        self.ptrs = [int(p) for p in self.hdl.buffer_ptrs]
         self.group = group
+        self.d1 = symm_mem.empty((self.rows_max, self.ld), dtype=torch.float32, device=device)
+        self.hdl = symm_mem.rendezvous(self.d1, group.group_name)
+        self.d1_ptrs = [int(p) for p in self.hdl.buffer_ptrs]
+        self.small = symm_mem.empty((self.small_bytes,), dtype=torch.uint8, device=device)
+        self.small.zero_()
+        self.hdl_small = symm_mem.rendezvous(self.small, group.group_name)
+        self.small_ptrs = [int(p) for p in self.hdl_small.buffer_ptrs]
+        self.hdl.barrier(channel=0)                    # every rank's zero fill is done before anyone pushes
 
-    def core(self, r: int):
-        """Disjoint cover of the frame rows: the rows whose distances rank r is responsible for."""
-        p = self.plans[r]
-        return p.a0 * self.stride, (self.n if r == self.world - 1 else p.a1 * self.stride)
+    def barrier(self, channel: int):
+        self.hdl.barrier(channel=channel)
 
-    def D1(self) -> torch.Tensor:
-        p = self.plan
-        return self.buf[:p.r_hi - p.r_lo, :self.n]
-
-    def jobs(self):
-        me, p = self.rank, self.plan
-        lo, hi = self.core(me)
-        mine = dict(D=self.ptrs[me], d_row0=p.r_lo, ldd=self.ld)
-        out = [dict(row0=lo, rows=hi - lo, col0=lo, cols=hi - lo, symmetric=1, count_stats=1,
-                    DT=self.ptrs[me], dt_row0=p.r_lo, ldt=self.ld, **mine)]
-        # peers are visited in rotated order (me+1, me+2, ...): at any moment every rank pushes into a
-        # DIFFERENT destination, instead of all ranks hammering rank 0's NVLink ingress first, then rank 1's...
-        for step in range(1, self.world):
-            other = (me + step) % self.world
-            olo, ohi = self.core(other)
-            peer = dict(DT=self.ptrs[other], dt_row0=self.plans[other].r_lo, ldt=self.ld)
-            if me < other:                                  # my rows x the first half of the peer's columns
-                mid = pair_split(olo, ohi)
-                if mid > olo:
-                    out.append(dict(row0=lo, rows=hi - lo, col0=olo, cols=mid - olo, symmetric=0, count_stats=1,
-                                    **peer, **mine))
-            else:                                           # the second half of my rows x the peer's columns
-                mid = pair_split(lo, hi)
-                if hi > mid:
-                    out.append(dict(row0=mid, rows=hi - mid, col0=olo, cols=ohi - olo, symmetric=0, count_stats=1,
-                                    **peer, **mine))
-        return out
-
-    def halo_rows(self) -> int:
-        """Rows past this rank's core that its filter outputs read: the next rank's first rows."""
-        return self.plan.r_hi - self.core(self.rank)[1]
-
-    def gram(self, pf: engine.PackedFrames, stats=None) -> torch.Tensor:
-        """Fills this rank's D1 shard (its own tiles + the tiles peers push).  Stream-ordered barriers on
-        both sides: peers must be done reading the previous contents, and done pushing, respectively."""
-        self.hdl.barrier(channel=0)
-        engine.gram_l2_jobs(pf, self.jobs(), stats)
-        self.hdl.barrier(channel=1)
-        halo = self.halo_rows()
-        if halo > 0:
-            # the halo rows are the first core rows of the next rank: one small peer copy over NVLink
-            # (fs rows) instead of fs-row MMA tiles that would waste 216 of their 256 rows
-            p, nxt = self.plan, self.rank + 1
-            src = self.hdl.get_buffer(nxt, (halo, self.ld), torch.float32)
-            lo = self.core(self.rank)[1] - p.r_lo
-            self.buf[lo:lo + halo].copy_(src)
-        return self.D1()
+    def peer_d1_rows(self, r: int, row_off: int, rows: int) -> torch.Tensor:
+        buf = self.hdl.get_buffer(r, (self.rows_max, self.ld), torch.float32)
+        return buf[row_off:row_off + rows]
 
 
-class PeerFutureCost:
-    """Symmetric-memory workspace + driver of avtex_future_cost_fused_peer: the whole row-sharded
-    future-cost iteration in one cooperative kernel per GPU, exchanging the row minima by peer stores."""
-    MAX_SWEEPS = 254
+class RankStep:
+    """One rank's classic++ step, phase by phase.  Phases of different ranks are separated by barriers (real
+    ranks) or by program order (virtual ranks on one device)."""
 
-    def __init__(self, m: int, rank: int, world: int, device, group=None):
-        import torch.distributed._symmetric_memory as symm_mem
-        self.m, self.rank, self.world = m, rank, world
-        self.mpad = (m + 31) // 32 * 32
-        self.n_m = 6 * self.mpad * 4                                   # two sets of three fp32 vectors
-        self.n_eps = (self.MAX_SWEEPS + 1) * world * 8
-        total = self.n_m + self.n_eps + 256
-        group = dist.group.WORLD if group is None else group
-        self.buf = symm_mem.empty((total,), dtype=torch.uint8, device=device)
-        self.buf.zero_()
-        self.hdl = symm_mem.rendezvous(self.buf, group.group_name)
-        self.hdl.barrier(channel=0)
-        self.base = [int(p) for p in self.hdl.buffer_ptrs]
-        self.calls = 0
-        self.device = device
+    def __init__(self, pb: PeerBuffers, frames: torch.Tensor, p: float = 0.7, alpha: float = 0.997,
+                 max_ctas: int = 0, timing: bool = False):
+        self.pb, self.frames, self.p, self.alpha, self.max_ctas = pb, frames, p, alpha, max_ctas
+        x = frames.reshape(frames.shape[0], -1)
+        if x.dtype != torch.uint8 or x.stride(1) != 1 or x.stride(0) % 16 != 0 or x.data_ptr() % 16 != 0:
+            raise engine._lib.AvtexError("sharded path needs contiguous uint8 frames with 16-byte aligned rows")
+        self.x = x
+        self.parity = pb.calls % 2
+        self.call = pb.calls
+        pb.calls += 1
+        self.marks = [] if timing else None
+        self.res = None
 
-    def run(self, D3_own: torch.Tensor, row0: int, alpha: float = 0.997, verbose: bool = False):
-        import ctypes as C
-        import numpy as np
-        from . import _lib
-        rows = D3_own.shape[0]
-        parity = self.calls % 2
-        arr = C.c_void_p * self.world
-        mptr = arr(*[b + parity * 3 * self.mpad * 4 for b in self.base])
-        eptr = arr(*[b + self.n_m for b in self.base])
-        fptr = arr(*[b + self.n_m + self.n_eps for b in self.base])
-        eps_local = torch.zeros(self.MAX_SWEEPS + 1, dtype=torch.float64, device=self.device)
-        trail = torch.zeros(self.MAX_SWEEPS + 1, dtype=torch.float64, device=self.device)
-        info = torch.zeros(2, dtype=torch.int32, device=self.device)
-        epoch = (self.calls * (self.MAX_SWEEPS + 2)) & 0xFFFFFFFF
-        _lib.call("avtex_future_cost_fused_peer", _lib.ptr(D3_own), D3_own.stride(0), row0, rows, self.m,
-                  C.c_float(engine._f32(alpha)), C.c_float(np.float32(engine.F32_EPS_STOP)), self.MAX_SWEEPS,
-                  self.rank, self.world, mptr, self.mpad, eptr, fptr, C.c_uint(epoch), _lib.ptr(eps_local),
-                  _lib.ptr(trail), _lib.ptr(info), engine._dev(D3_own), engine._stream(D3_own))
-        self.calls += 1
-        n_sweeps, idx = (int(v) for v in info.cpu())
-        if n_sweeps == 0:
-            raise RuntimeError("future cost did not converge")
-        m_all = self.buf[:self.n_m].view(torch.float32)
-        off = (parity * 3 + idx) * self.mpad
-        eps = [float(np.float32(v / (float(self.m) ** 2))) for v in trail[1:n_sweeps + 1].cpu()]
-        if verbose:
-            for e in eps:
-                print("Eps:", f"tensor({e:.4f})")
-        return engine.FutureCostResult(m_all[off:off + self.m], n_sweeps, eps, n_sweeps + 1)
+    def mark(self, name):
+        if self.marks is not None:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            self.marks.append((name, ev))
+
+    # -- K0: my slice of the norms, pushed to every rank's vector
+    def norms(self):
+        pb = self.pb
+        n, k = self.x.shape
+        per = -(-n // pb.world)
+        lo, hi = pb.rank * per, min(n, (pb.rank + 1) * per)
+        sq_off = pb.off_sq + self.parity * pb.npad * 8
+        fl_off = pb.off_fl + self.parity * 16
+        self.static_ok = (k + 127) // 128 * 128 * 128 * 128 < engine.GRAM_MAX_SQNORM
+        # the other parity's max flag is idle now (last read at the end of the previous call, next pushed into
+        # after this call's barriers): reset it for the next call
+        pb.flags(1 - self.parity).zero_()
+        if hi > lo:
+            engine.frame_norms_push(self.x, lo, hi - lo, [b + sq_off for b in pb.small_ptrs],
+                                    None if self.static_ok else [b + fl_off + 8 for b in pb.small_ptrs])
+        self.pf = engine.PackedFrames(self.x, pb.sqnorm(self.parity)[:n], k, pb.flags(self.parity), signed=False)
+        if self.static_ok:
+            self.pf._checked = (True, "")
+
+    # -- K1: my tiles, transposes pushed into the peers' shards
+    def gram(self):
+        pb = self.pb
+        engine.gram_l2_jobs(self.pf, symmetric_jobs(pb.plans, pb.rank, pb.d1_ptrs, pb.ld, pb.stride))
+
+    def halo(self):
+        pb = self.pb
+        p = pb.plan
+        for owner, row, rows in halo_sources(pb.plans, pb.rank, pb.stride):
+            src = pb.peer_d1_rows(owner, row - pb.plans[owner].r_lo, rows)
+            pb.d1[row - p.r_lo: row - p.r_lo + rows].copy_(src)
+        self.D1 = pb.D1()
+
+    # -- K2
+    def filter(self):
+        pb = self.pb
+        p = pb.plan
+        self.D2, self.D3 = engine.diag_filter(self.D1, pb.fs, pb.stride, p=self.p, m=p.m, a0=p.a0,
+                                              rows_out=p.a1h - p.a0, in_row0=p.r_lo)
+
+    # -- K3: all sweeps + their exchanges in one cooperative kernel
+    def future_cost(self):
+        pb = self.pb
+        p = pb.plan
+        own = p.a1 - p.a0
+        dev = pb.device
+        arr = C.c_void_p * pb.world
+        mptr = arr(*[b + pb.off_m + self.parity * 3 * pb.mpad * 4 for b in pb.small_ptrs])
+        eptr = arr(*[b + pb.off_eps + self.parity * pb.n_eps for b in pb.small_ptrs])
+        fptr = arr(*[b + pb.off_sweep for b in pb.small_ptrs])
+        scratch = torch.zeros(2 * (pb.MAX_SWEEPS + 1), dtype=torch.float64, device=dev)
+        eps_local, trail = scratch[:pb.MAX_SWEEPS + 1], scratch[pb.MAX_SWEEPS + 1:]
+        info = torch.zeros(4, dtype=torch.int32, device=dev)
+        self.m_out = torch.empty(pb.mpad, dtype=torch.float32, device=dev)
+        epoch = (self.call * (pb.MAX_SWEEPS + 2)) & 0xFFFFFFFF
+        D3_own = self.D3[:own]
+        _lib.call("avtex_future_cost_fused_peer", _lib.ptr(D3_own), D3_own.stride(0), p.a0, own, p.m,
+                  C.c_float(engine._f32(self.alpha)), C.c_float(np.float32(engine.F32_EPS_STOP)), pb.MAX_SWEEPS,
+                  pb.rank, pb.world, mptr, pb.mpad, eptr, fptr, C.c_uint(epoch), _lib.ptr(eps_local),
+                  _lib.ptr(trail), _lib.ptr(info), _lib.ptr(self.m_out), self.max_ctas, engine._dev(D3_own),
+                  engine._stream(D3_own))
+        self.fc = engine.FutureCostResult(self.m_out[:p.m], pending=(info, trail, p.m, None))
+
+    # -- K4 (+ sigma statistics of my rows)
+    def finalize(self, want_stats: bool):
+        p = self.pb.plan
+        own = p.a1 - p.a0
+        self.stats = engine.new_stats(self.pb.device) if want_stats else None
+        if want_stats and p.a1h > p.a1:
+            # statistics cover the OWNED rows only: the halo row is finalized by a second, stat-less launch
+            self.D3_new = engine.empty_matrix(p.a1h - p.a0, p.m, self.pb.device)
+            _finalize_into(self.D3[:own], self.fc.mvec, self.alpha, p.a0, p.m, self.D3_new[:own], self.stats)
+            _finalize_into(self.D3[own:], self.fc.mvec, self.alpha, p.a1, p.m, self.D3_new[own:], None)
+        else:
+            self.D3_new = engine.future_cost_finalize(self.D3, self.fc.mvec, self.alpha, row0=p.a0, m=p.m,
+                                                      stats=self.stats)
+
+    def result(self) -> "ShardResult":
+        res = ShardResult(self.pb.plan, self.D1, self.D2, self.D3, self.D3_new, self.fc)
+        res.launches = 1 + 1 + 1 + 1 + 1
+        if self.marks is not None:
+            torch.cuda.synchronize()
+            res.stage_ms = {b[0]: a[1].elapsed_time(b[1]) for a, b in zip(self.marks[:-1], self.marks[1:])}
+        return res
+
+
+def _finalize_into(D3, mvec, alpha, row0, m, out, stats):
+    s, z = engine._stats_ptrs(stats)
+    _lib.call("avtex_future_cost_finalize", _lib.ptr(D3), D3.stride(0), row0, D3.shape[0], m, _lib.ptr(mvec),
+              C.c_float(engine._f32(alpha)), _lib.ptr(out), out.stride(0), s, z, engine._dev(D3), engine._stream(D3))
 
 
 @dataclass
@@ -262,85 +396,224 @@ class ShardResult:
     D2: torch.Tensor          # rows [a0, a1h)
     D3: torch.Tensor
     D3_new: torch.Tensor      # rows [a0, a1h)
-    n_sweeps: int
-    eps_trail: list
+    fc: engine.FutureCostResult | None = None
     sigma: float | None = None
     P3: torch.Tensor | None = None        # rows [a0, a1)
     P3_new: torch.Tensor | None = None
     counts: torch.Tensor | None = None
     launches: int = 0
-    stage_ms: dict | None = None          # CUDA-event stage times when AVTEX_DIST_TIMING=1
+    stage_ms: dict | None = None          # CUDA-event stage times (timing=True / AVTEX_DIST_TIMING=1)
+
+    @property
+    def n_sweeps(self) -> int:            # reads the device on first use (one small D2H)
+        return self.fc.n_sweeps
+
+    @property
+    def eps_trail(self) -> list:
+        return self.fc.eps_trail
+
+
+def _probabilities(res: ShardResult, stats: torch.Tensor, sigma_factor, threshold):
+    own = res.plan.a1 - res.plan.a0
+    res.sigma = engine.sigma_from_stats(*engine.read_stats(stats), sigma_factor)
+    res.P3, res.P3_new, res.counts = engine.transition_probs(
+        res.D3_new, res.sigma, shift=1, rows_out=own, threshold=threshold, want_counts=threshold is not None)
+    res.launches += 1
 
 
 def classic_sharded(frames: torch.Tensor, filter_size: int, stride: int, rank: int, world: int,
                     p: float = 0.7, alpha: float = 0.997, sigma_factor=None, threshold=None, group=None,
                     packed: engine.PackedFrames | None = None,
-                    workspace: SymmetricShardWorkspace | None = None,
-                    peer_fc: PeerFutureCost | None = None) -> ShardResult:
+                    workspace: SymmetricShardWorkspace | None = None, timing: bool | None = None) -> ShardResult:
     """Distance + filter + converged future cost (+ sigma3 / P3 / P3_new when sigma_factor is given) for
     this rank's rows.  `frames`: the full [N, ...] uint8 clip on this rank's device.  With a
-    SymmetricShardWorkspace the distance stage uses the symmetry across ranks (peer pushes over NVLink);
-    without one every rank computes its full row block locally."""
+    SymmetricShardWorkspace every exchange happens inside the kernels (module docstring) and the host never
+    synchronises before the step's results are read; without one every rank computes its full row block
+    locally and the future cost exchanges through NCCL (`make_exchange`)."""
     import os
-    timing = os.environ.get("AVTEX_DIST_TIMING") == "1"
-    marks = []
-
-    def mark(name):
-        if timing:
-            ev = torch.cuda.Event(enable_timing=True)
-            ev.record()
-            marks.append((name, ev))
-
+    if timing is None:
+        timing = os.environ.get("AVTEX_DIST_TIMING") == "1"
     n = frames.shape[0]
     plan = plan_shards(n, filter_size, stride, world, rank)
-    mark("start")
-    pf = pack_frames_sharded(frames, rank, world, group) if packed is None else packed
-    mark("norms")
-    if not pf.exact_ok:
-        raise engine._lib.AvtexError(f"sharded path needs byte frames inside the Gram domain: {pf.reason}")
     if workspace is not None and world > 1:
-        D1 = workspace.gram(pf)                            # symmetric across ranks: transposed tiles pushed to peers
+        st = RankStep(workspace, frames, p, alpha, timing=timing)
+        st.mark("start")
+        st.norms()
+        st.mark("norms")
+        workspace.barrier(0)               # norms of all ranks have landed; peers finished reading my old shard
+        st.gram()
+        workspace.barrier(1)               # all pushed tiles have landed
+        st.halo()
+        st.mark("gram")
+        st.filter()
+        st.mark("filter")
+        st.future_cost()
+        st.mark("future_cost")
+        st.finalize(want_stats=sigma_factor is not None)
+        st.mark("finalize")
+        res = st.result()
+        if not st.static_ok and not st.pf.exact_ok:       # deferred domain check (the Gram ran speculatively)
+            raise engine._lib.AvtexError(f"sharded path needs byte frames inside the Gram domain: {st.pf.reason}")
+        if sigma_factor is not None and res.fc._n_sweeps is None:
+            # results are about to be consumed: settle convergence now (first host read of the step).  A clip
+            # that needs more sweeps than the in-kernel cap finishes through the NCCL loop (all ranks take this
+            # branch together: the stop decision is identical everywhere).
+            try:
+                res.fc._resolve()
+            except RuntimeError as exc:
+                if "did not converge" not in str(exc):
+                    raise
+                own = plan.a1 - plan.a0
+                res.fc = engine.future_cost(st.D3[:own], alpha, row0=plan.a0, m=plan.m,
+                                            exchange=make_exchange(plan, group), pad_to=plan.padded)
+                st.fc = res.fc
+                st.finalize(want_stats=True)
+                res.D3_new = st.D3_new
+        stats = st.stats
     else:
+        marks = [] if timing else None
+
+        def mark(name):
+            if marks is not None:
+                ev = torch.cuda.Event(enable_timing=True)
+                ev.record()
+                marks.append((name, ev))
+
+        mark("start")
+        pf = pack_frames_sharded(frames, rank, world, group) if packed is None else packed
+        mark("norms")
         D1 = engine.gram_l2(pf, plan.r_lo, plan.r_hi - plan.r_lo, symmetric=False)
-    mark("gram")
-    D2, D3 = engine.diag_filter(D1, filter_size, stride, p=p, m=plan.m, a0=plan.a0,
-                                rows_out=plan.a1h - plan.a0, in_row0=plan.r_lo)
-    own = plan.a1 - plan.a0
-    mark("filter")
-    if peer_fc is not None and world > 1:
-        fc = peer_fc.run(D3[:own], plan.a0, alpha)         # all sweeps + exchanges inside one kernel per GPU
-        n_fc_launches = 1
-    else:
+        mark("gram")
+        D2, D3 = engine.diag_filter(D1, filter_size, stride, p=p, m=plan.m, a0=plan.a0,
+                                    rows_out=plan.a1h - plan.a0, in_row0=plan.r_lo)
+        own = plan.a1 - plan.a0
+        mark("filter")
         fc = engine.future_cost(D3[:own], alpha, row0=plan.a0, m=plan.m, exchange=make_exchange(plan, group),
                                 pad_to=plan.padded)
-        n_fc_launches = fc.passes
-    res = ShardResult(plan, D1, D2, D3, None, fc.n_sweeps, fc.eps_trail)
-    res.launches = 1 + 1 + 1 + n_fc_launches + 1
-    mark("future_cost")
-    res.D3_new = engine.future_cost_finalize(D3, fc.mvec, alpha, row0=plan.a0, m=plan.m)
-    mark("finalize")
-    if timing:
-        torch.cuda.synchronize()
-        res.stage_ms = {b[0]: a[1].elapsed_time(b[1]) for a, b in zip(marks[:-1], marks[1:])}
+        mark("future_cost")
+        stats = engine.new_stats(frames.device) if sigma_factor is not None else None
+        if stats is not None and plan.a1h > plan.a1:
+            D3_new = engine.empty_matrix(plan.a1h - plan.a0, plan.m, frames.device)
+            _finalize_into(D3[:own], fc.mvec, alpha, plan.a0, plan.m, D3_new[:own], stats)
+            _finalize_into(D3[own:], fc.mvec, alpha, plan.a1, plan.m, D3_new[own:], None)
+        else:
+            D3_new = engine.future_cost_finalize(D3, fc.mvec, alpha, row0=plan.a0, m=plan.m, stats=stats)
+        mark("finalize")
+        res = ShardResult(plan, D1, D2, D3, D3_new, fc)
+        res.launches = 1 + 1 + 1 + fc.passes + 1
+        if marks is not None:
+            torch.cuda.synchronize()
+            res.stage_ms = {b[0]: a[1].elapsed_time(b[1]) for a, b in zip(marks[:-1], marks[1:])}
+        if not pf.exact_ok:
+            raise engine._lib.AvtexError(f"sharded path needs byte frames inside the Gram domain: {pf.reason}")
     if sigma_factor is not None:
-        stats = engine.sum_nnz(res.D3_new[:own])
         if world > 1:
             stats = allreduce_stats(stats, group)
-        res.sigma = engine.sigma_from_stats(*engine.read_stats(stats), sigma_factor)
-        res.P3, res.P3_new, res.counts = engine.transition_probs(
-            res.D3_new, res.sigma, shift=1, rows_out=own, threshold=threshold, want_counts=threshold is not None)
-        res.launches += 2
+        _probabilities(res, stats, sigma_factor, threshold)
     return res
 
 
 def gather_survivors(res: ShardResult, group=None):
-    """CSR of P3_new over all ranks, assembled on every rank (the walk runs on rank 0's host)."""
-    rowptr, colidx = engine.csr_from_matrix(res.P3_new, res.counts)
-    if res.plan.world == 1:
-        return rowptr, colidx
-    parts = [None] * res.plan.world
-    dist.all_gather_object(parts, (rowptr, colidx), group=group)
-    import numpy as np
-    counts = np.concatenate([np.diff(rp) for rp, _ in parts])
-    full_ptr = np.concatenate(([0], np.cumsum(counts))).astype(np.int64)
-    return full_ptr, np.concatenate([ci for _, ci in parts])
+    """CSR of P3_new over all ranks, assembled on every rank (the walk runs on rank 0's host): row counts
+    and column lists travel as two padded NCCL all-gathers on the device, then ONE D2H copy."""
+    world = res.plan.world
+    if world == 1:
+        return engine.csr_from_matrix(res.P3_new, res.counts)
+    dev = res.P3_new.device
+    plan = res.plan
+    own = plan.a1 - plan.a0
+    counts = torch.zeros(plan.shard, dtype=torch.int32, device=dev)
+    counts[:own] = res.counts
+    all_counts = torch.empty(world * plan.shard, dtype=torch.int32, device=dev)
+    dist.all_gather_into_tensor(all_counts, counts, group=group)
+    per_rank = all_counts.view(world, plan.shard).sum(1)
+    cap = int(per_rank.max().item())                               # one small sync: the padded length
+    rowptr = torch.zeros(own + 1, dtype=torch.int64, device=dev)
+    torch.cumsum(res.counts, 0, out=rowptr[1:])
+    colidx = torch.zeros(max(cap, 1), dtype=torch.int32, device=dev)
+    _lib.call("avtex_csr_fill", _lib.ptr(res.P3_new), res.P3_new.stride(0), own, res.P3_new.shape[1],
+              _lib.ptr(rowptr), _lib.ptr(colidx), engine._dev(res.P3_new), engine._stream(res.P3_new))
+    all_cols = torch.empty(world * max(cap, 1), dtype=torch.int32, device=dev)
+    dist.all_gather_into_tensor(all_cols, colidx, group=group)
+    h_counts = all_counts.cpu().numpy().reshape(world, plan.shard)
+    h_cols = all_cols.cpu().numpy().reshape(world, max(cap, 1))
+    counts_list, cols_list = [], []
+    for r in range(world):
+        a0 = r * plan.shard
+        own_r = min(plan.m, a0 + plan.shard) - a0
+        c = h_counts[r, :own_r]
+        counts_list.append(c)
+        cols_list.append(h_cols[r, :int(c.sum())])
+    full_counts = np.concatenate(counts_list)
+    full_ptr = np.concatenate(([0], np.cumsum(full_counts, dtype=np.int64))).astype(np.int64)
+    return full_ptr, np.concatenate(cols_list)
+
+
+# --------------------------------------------------------------------------- virtual ranks on one device
+class _VirtualRankBuffers(PeerBuffers):
+    def __init__(self, box: "VirtualBox", rank: int):
+        super().__init__(box.n, box.fs, box.stride, rank, box.world, box.device)
+        self.box = box
+
+    def barrier(self, channel: int):
+        pass                                          # program order on one stream separates the phases
+
+    def peer_d1_rows(self, r: int, row_off: int, rows: int) -> torch.Tensor:
+        return self.box.ranks[r].d1[row_off:row_off + rows]
+
+
+class VirtualBox:
+    """G "virtual ranks" on ONE device: every rank has its own shard buffers (plain allocations), the peer
+    pointers handed to the kernels are the other ranks' local buffers, and the phases of a step run rank by
+    rank in program order.  The same job lists, halo plans, norm pushes and — with the G cooperative kernels
+    co-resident on G streams — the same flag barrier as on a real 8-GPU box, so tests/test_gpu_virtual.py
+    checks the G = 2 / 4 / 8 paths bit-for-bit against the single-GPU pipeline on a 1-GPU machine."""
+
+    def __init__(self, n: int, filter_size: int, stride: int, world: int, device):
+        self.n, self.fs, self.stride, self.world, self.device = n, filter_size, stride, world, device
+        self.ranks = [_VirtualRankBuffers(self, r) for r in range(world)]
+        for pb in self.ranks:
+            pb.d1 = torch.empty((pb.rows_max, pb.ld), dtype=torch.float32, device=device)
+            pb.small = torch.zeros(pb.small_bytes, dtype=torch.uint8, device=device)
+        for pb in self.ranks:
+            pb.d1_ptrs = [q.d1.data_ptr() for q in self.ranks]
+            pb.small_ptrs = [q.small.data_ptr() for q in self.ranks]
+        self.streams = [torch.cuda.Stream(device) for _ in range(world)]
+
+    def step(self, frames: torch.Tensor, sigma_factor=None, threshold=None, p: float = 0.7, alpha: float = 0.997):
+        """Returns the list of per-rank ShardResults (sigma / P3 / P3_new filled when sigma_factor is given)."""
+        steps = [RankStep(pb, frames, p, alpha, max_ctas=-self.world) for pb in self.ranks]
+        for phase in ("norms", "gram", "halo", "filter"):
+            for st in steps:
+                getattr(st, phase)()
+        # the G cooperative kernels spin on each other's flags: they must run CONCURRENTLY (one stream each,
+        # grids capped so that all are resident)
+        main = torch.cuda.current_stream(self.device)
+        done = []
+        for st, stream in zip(steps, self.streams):
+            stream.wait_stream(main)
+            with torch.cuda.stream(stream):
+                st.future_cost()
+                ev = torch.cuda.Event()
+                ev.record(stream)
+                done.append(ev)
+        for ev in done:
+            main.wait_event(ev)
+        out = []
+        for st in steps:
+            st.finalize(want_stats=sigma_factor is not None)
+            out.append(st.result())
+        if sigma_factor is not None:
+            total = torch.zeros(2, dtype=torch.float64, device=self.device)
+            total[0] = sum(st.stats[0] for st in steps)
+            total.view(torch.int64)[1] = sum(st.stats.view(torch.int64)[1] for st in steps)
+            for res in out:
+                _probabilities(res, total, sigma_factor, threshold)
+        return out
+
+
+def virtual_survivors(results: list):
+    """CSR of P3_new assembled from the virtual ranks' shards."""
+    ptrs, cols = zip(*(engine.csr_from_matrix(r.P3_new, r.counts) for r in results))
+    counts = np.concatenate([np.diff(p) for p in ptrs])
+    return np.concatenate(([0], np.cumsum(counts))).astype(np.int64), np.concatenate(cols)

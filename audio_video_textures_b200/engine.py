@@ -8,7 +8,7 @@ PyTorch arithmetic: a missing library or a failed kernel raises.
 from __future__ import annotations
 
 import ctypes as C
-from dataclasses import dataclass, field
+from dataclasses import dataclass
 
 import numpy as np
 import torch
@@ -157,6 +157,19 @@ def frame_norms_rows(frames_u8: torch.Tensor, row0: int, rows: int, sqnorm: torc
               _stream(frames_u8))
 
 
+def frame_norms_push(frames_u8: torch.Tensor, row0: int, rows: int, sqnorm_ptrs: list, max_ptrs: list | None):
+    """K0 on rows [row0, row0+rows) of raw uint8 frames, results written to EVERY destination vector in
+    `sqnorm_ptrs` (raw device pointers of the full [N] int64 vector on each GPU, peer-mapped) and the centred
+    maximum raised in `max_ptrs`: the row-sharded path pushes its slice of the norms to all peers from the
+    kernel instead of all-gathering afterwards."""
+    part = frames_u8[row0:row0 + rows]
+    n_dst = len(sqnorm_ptrs)
+    sq = (C.c_void_p * n_dst)(*sqnorm_ptrs)
+    mx = (C.c_void_p * n_dst)(*max_ptrs) if max_ptrs is not None else None
+    _lib.call("avtex_frame_norms_u8_push", _lib.ptr(part), rows, frames_u8.shape[1], frames_u8.stride(0), row0,
+              sq, mx, n_dst, _dev(frames_u8), _stream(frames_u8))
+
+
 def gram_l2(pf: PackedFrames, row0: int = 0, rows: int | None = None, symmetric: bool | None = None,
             stats: torch.Tensor | None = None, out: torch.Tensor | None = None) -> torch.Tensor:
     """K1 on tensor cores.  Returns D[rows, N] for global rows [row0, row0+rows)."""
@@ -175,9 +188,11 @@ def gram_l2(pf: PackedFrames, row0: int = 0, rows: int | None = None, symmetric:
     return D
 
 
-def gram_l2_jobs(pf: PackedFrames, jobs: list, stats: torch.Tensor | None = None, device=None):
+def gram_l2_jobs(pf: PackedFrames, jobs: list, stats: torch.Tensor | None = None, device=None,
+                 clock_probe: torch.Tensor | None = None):
     """K1, general form: `jobs` is a list of dicts with the fields of AvtexGramJob (D / DT are raw device
-    pointers, possibly into a peer GPU's symmetric-memory buffer)."""
+    pointers, possibly into a peer GPU's symmetric-memory buffer).  `clock_probe`: int64[2] on the device,
+    receives (SM cycles, nanoseconds) of CTA 0's tile loop (bench.py's in-kernel clock measurement)."""
     arr = (_lib.GramJob * len(jobs))()
     for dst, j in zip(arr, jobs):
         dst.row0, dst.rows, dst.col0, dst.cols = j["row0"], j["rows"], j["col0"], j["cols"]
@@ -188,7 +203,7 @@ def gram_l2_jobs(pf: PackedFrames, jobs: list, stats: torch.Tensor | None = None
     s, z = _stats_ptrs(stats)
     k_extent = pf.packed.shape[1] if pf.signed else pf.k
     _lib.call("avtex_gram_l2_jobs", _lib.ptr(pf.packed), 1 if pf.signed else 0, n, k_extent, pf.packed.stride(0),
-              _lib.ptr(pf.sqnorm), arr, len(jobs), s, z, _dev(pf.packed), _stream(pf.packed))
+              _lib.ptr(pf.sqnorm), arr, len(jobs), s, z, _lib.ptr(clock_probe), _dev(pf.packed), _stream(pf.packed))
 
 
 def pairwise_l2_from_host(frames: torch.Tensor, device=None, stats: torch.Tensor | None = None, chunks: int = 8):
@@ -339,12 +354,48 @@ def diag_filter(D1: torch.Tensor, filter_size: int, stride: int = 1, p: float | 
 
 
 # --------------------------------------------------------------------------- K3 / K4
-@dataclass
 class FutureCostResult:
-    mvec: torch.Tensor            # [M (padded)] fp32: D3_new = D3 + fl(alpha*mvec) on rows >= 1
-    n_sweeps: int                 # == number of `Eps:` lines the reference prints
-    eps_trail: list = field(default_factory=list)
-    passes: int = 0               # streaming reads of D3 actually performed (n_sweeps + 1)
+    """Result of the future-cost iteration.  `mvec` ([M (padded)] fp32: D3_new = D3 + fl(alpha*mvec) on rows >= 1)
+    is available immediately (stream-ordered); `n_sweeps` (== number of `Eps:` lines the reference prints),
+    `eps_trail` and `passes` (streaming reads of D3 performed = n_sweeps + 1) of the fused kernels are read from
+    the device lazily, so a caller that only needs `mvec` launches the next kernel without a host sync."""
+
+    def __init__(self, mvec, n_sweeps=None, eps_trail=None, passes=0, pending=None):
+        self.mvec = mvec
+        self._n_sweeps, self._eps_trail, self._passes, self._pending = n_sweeps, eps_trail, passes, pending
+
+    def _resolve(self):
+        if self._pending is not None:
+            info, trail, m, on_fail = self._pending
+            self._pending = None
+            h = [int(v) for v in info.cpu()]
+            if len(h) > 2 and h[2] != 0:
+                raise RuntimeError("future cost: a peer GPU did not reach the sweep barrier (timeout)")
+            if h[0] == 0:
+                if on_fail is None:
+                    raise RuntimeError("future cost did not converge")
+                other = on_fail()
+                self.mvec.copy_(other.mvec[:self.mvec.shape[0]])
+                self._n_sweeps, self._eps_trail, self._passes = other.n_sweeps, other.eps_trail, other.passes
+                return
+            self._n_sweeps = h[0]
+            self._eps_trail = [float(np.float32(v / (float(m) * float(m)))) for v in trail[1:h[0] + 1].cpu()]
+            self._passes = h[0] + 1
+
+    @property
+    def n_sweeps(self) -> int:
+        self._resolve()
+        return self._n_sweeps
+
+    @property
+    def eps_trail(self) -> list:
+        self._resolve()
+        return self._eps_trail
+
+    @property
+    def passes(self) -> int:
+        self._resolve()
+        return self._passes
 
 
 def future_cost(D3: torch.Tensor, alpha: float = 0.997, row0: int = 0, m: int | None = None,
@@ -393,23 +444,30 @@ def future_cost(D3: torch.Tensor, alpha: float = 0.997, row0: int = 0, m: int | 
 
 def future_cost_fused(D3: torch.Tensor, alpha: float = 0.997, verbose: bool = False,
                       max_sweeps: int = 4096) -> FutureCostResult:
-    """K3, all sweeps in one cooperative launch (single GPU): no host round trip per sweep."""
+    """K3, all sweeps in one cooperative launch (single GPU): no host round trip per sweep, and none after the
+    launch either — the converged vector lands in a fixed buffer, sweep count / eps trail are read on demand."""
     m = D3.shape[1]
     mpad = (m + 31) // 32 * 32
-    mbuf = torch.zeros(3 * mpad, dtype=torch.float32, device=D3.device)
+    mbuf = torch.zeros(4 * mpad, dtype=torch.float32, device=D3.device)          # 3 rotating vectors + the result
     trail = torch.zeros(max_sweeps + 1, dtype=torch.float64, device=D3.device)
-    info = torch.zeros(2, dtype=torch.int32, device=D3.device)
+    info = torch.zeros(4, dtype=torch.int32, device=D3.device)
+    m_out = mbuf[3 * mpad:]
     _lib.call("avtex_future_cost_fused", _lib.ptr(D3), D3.stride(0), m, C.c_float(_f32(alpha)),
               C.c_float(np.float32(F32_EPS_STOP)), max_sweeps, _lib.ptr(mbuf), mpad, _lib.ptr(trail),
-              _lib.ptr(info), _dev(D3), _stream(D3))
-    n_sweeps, idx = (int(v) for v in info.cpu())
-    if n_sweeps == 0:
-        raise RuntimeError("future cost did not converge")
-    eps = [float(np.float32(v / (float(m) * float(m)))) for v in trail[1:n_sweeps + 1].cpu()]
+              _lib.ptr(info), _lib.ptr(m_out), _dev(D3), _stream(D3))
+    res = FutureCostResult(m_out[:m], pending=(info, trail, m, None))
     if verbose:
-        for e in eps:
+        for e in res.eps_trail:
             print("Eps:", f"tensor({e:.4f}, device='{D3.device}')")
-    return FutureCostResult(mbuf[idx * mpad: idx * mpad + m], n_sweeps, eps, n_sweeps + 1)
+    return res
+
+
+def pow_matrix(D: torch.Tensor, p: float) -> torch.Tensor:
+    """D ** p (classic/q_learning.py:34) into a fresh padded matrix."""
+    out = empty_matrix(D.shape[0], D.shape[1], D.device)
+    _lib.call("avtex_pow_matrix", _lib.ptr(D), D.stride(0), D.shape[0], D.shape[1], C.c_float(_f32(p)),
+              _lib.ptr(out), out.stride(0), _dev(D), _stream(D))
+    return out
 
 
 def future_cost_finalize(D3: torch.Tensor, mvec: torch.Tensor, alpha: float = 0.997, row0: int = 0,
@@ -445,6 +503,51 @@ def select_step(o: torch.Tensor, a: torch.Tensor | None, q: int, alpha: float, t
     _lib.call("avtex_select_step", _lib.ptr(o), _lib.ptr(a), o.shape[0], int(q), C.c_float(_f32(alpha)),
               C.c_float(np.float32(1.0 - float(alpha))), C.c_float(_f32(threshold)), _lib.ptr(choices),
               _lib.ptr(n_choices), _lib.ptr(vals), _dev(o), _stream(o))
+
+
+class SynthesisWorkspace:
+    """Scratch of avtex_synthesis_step for tables of L windows, incl. the mapped pinned result buffer."""
+
+    def __init__(self, L: int, device, host_cap: int = 4096):
+        self.L, self.host_cap = L, min(L, host_cap)
+        self.f32 = torch.empty(3 * L, dtype=torch.float32, device=device)
+        self.acc = torch.zeros(8, dtype=torch.float64, device=device)
+        self.mx = torch.zeros(2, dtype=torch.int32, device=device)
+        self.counts = torch.zeros(4096, dtype=torch.int32, device=device)
+        self.sel = torch.zeros(L + 1, dtype=torch.int32, device=device)         # [count | choices...]
+        self.host = torch.zeros(2 + self.host_cap, dtype=torch.int32).pin_memory()
+        self.host_np = self.host.numpy()
+        self.seq = 0
+
+
+def synthesis_step(ws: SynthesisWorkspace, tn: torch.Tensor, qrow: torch.Tensor, q: int, temp: float, alpha: float,
+                   threshold: float, sn: torch.Tensor | None = None, drow: torch.Tensor | None = None,
+                   vals: torch.Tensor | None = None) -> np.ndarray:
+    """K6 + K7 in ONE cooperative launch; returns the survivor window ids (int32, target-list order).  The kernel
+    writes the list into mapped pinned memory and the host polls the sequence word: no D2H copy call, no
+    stream synchronisation."""
+    ws.seq += 1
+    seq = ws.seq
+    _lib.call("avtex_synthesis_step", _lib.ptr(tn), tn.stride(0), tn.shape[0], tn.shape[1], _lib.ptr(qrow),
+              _lib.ptr(sn), sn.stride(0) if sn is not None else 0, sn.shape[1] if sn is not None else 0,
+              _lib.ptr(drow), C.c_float(_f32(temp)), int(q), C.c_float(_f32(alpha)),
+              C.c_float(np.float32(1.0 - float(alpha))), C.c_float(_f32(threshold)), _lib.ptr(ws.f32),
+              _lib.ptr(ws.acc), _lib.ptr(ws.mx), _lib.ptr(ws.counts), ws.counts.shape[0],
+              C.c_void_p(ws.sel.data_ptr() + 4), _lib.ptr(ws.sel), _lib.ptr(vals), _lib.ptr(ws.host), ws.host_cap,
+              seq, _dev(tn), _stream(tn))
+    h = ws.host_np
+    spins = 0
+    stream = torch.cuda.current_stream(tn.device)
+    while h[0] != seq:
+        spins += 1
+        if spins % 20000 == 0 and stream.query() and h[0] != seq:
+            torch.cuda.synchronize()                       # surfaces a launch / execution error if there was one
+            if h[0] != seq:
+                raise _lib.AvtexError("synthesis_step: the kernel finished without publishing its result")
+    n = int(h[1])
+    if n <= ws.host_cap:
+        return h[2:2 + n].copy()
+    return ws.sel[1:n + 1].cpu().numpy()
 
 
 def audio_start(x: torch.Tensor, d: torch.Tensor) -> int:

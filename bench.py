@@ -1,17 +1,30 @@
 #!/usr/bin/env python
 """bench.py — the classic++ transition-matrix hot path (distance + temporal filter + converged
-future cost) on synthetic video, per BASELINE.json: frame-pairs/s at N frames.
+future cost) on synthetic video, per BASELINE.json: frame-pairs/s at N frames; synth frames/s.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c1|c2|c5]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c1|c2|c5|hbm]
 
-N = 1   workload c2 = configs[1]: classic++ (-m 3, -fs 40, -stride 4) on a synthetic 5000-frame
-        224x224 RGB clip, one B200.
-N > 1   (torchrun, one rank per GPU) the same clip shape with N_frames = 5000*sqrt(N): per-GPU
-        frame-pairs are constant ("weak"), rows sharded, all-gather of the per-row minima per sweep.
-One "step" = pack (K0) -> tcgen05 Gram + L2 epilogue (K1) -> diagonal filter + pow (K2) -> future-cost
-sweeps to convergence (K3, host reads eps each sweep) -> finalize (K4).  `value` is timed with the byte
-frames resident in HBM; `e2e` goes through the reference-named entry points (compute_D1 / compute_D2 /
-q_learning + the survivor lists for the walk) from PINNED HOST frames, copies inside the timed region.
+Main line
+  N = 1   workload c2 = configs[1]: classic++ (-m 3, -fs 40, -stride 4) on a synthetic 5000-frame
+          224x224 RGB clip, one B200.
+  N > 1   (torchrun, one rank per GPU) the same clip shape with N_frames = 5000*sqrt(N): per-GPU
+          frame-pairs are constant ("weak"); rows sharded; every exchange (norms, transposed Gram tiles,
+          per-sweep row minima) is a peer store from inside the kernels (dist.py).
+  One "step" = norms (K0) -> tcgen05 Gram + L2 epilogue (K1) -> diagonal filter + pow (K2) -> all future-cost
+  sweeps in one cooperative kernel (K3) -> finalize (K4).  `value` is timed with the byte frames resident in
+  HBM; `e2e` goes through the reference-named entry points from PINNED HOST frames and includes sigma3 / P3 /
+  P3_new and the survivor lists copied back to the host — the SAME scope at every N.
+Extra records on the same JSON line (all measured in this run)
+  roofline      the Gram kernel: executed int8 ops against an int8 peak MEASURED here (cuBLASLt int8 GEMM and a
+                long-K run of the kernel itself), algorithmic ops separately, the SM clock measured INSIDE the
+                kernel (clock64 / globaltimer), DRAM traffic from the committed ncu launch list
+  roofline_hbm  (N = 1) the HBM-bound kernels at M = 19961 (1.6 GB matrices, far beyond L2)
+  extra.c5      configs[4], the north-star size: 100000 frames 64x64, -m 3, at THIS N (strong scaling from
+                the N = 1 run of the same clip), with per-stage times (max over ranks) and its own e2e
+  extra.parity  (N > 1) shards of the row-sharded pipeline == the single-GPU pipeline on a 3000-frame clip
+  extra.synth   (N = 1) `synth frames/s`: the classic walk over the survivor lists, and contrastive synthesis
+                C3 / C4 (20000 windows, D = 2304, A = 128 / 12288) ms per step and frames/s
+  stages        (N > 1) norms / gram / filter / future_cost / finalize of the main workload, max over ranks
 `--impl reference` / `cpu_baseline` time the CPU oracle port of the reference algorithm on a bounded
 sample (see cpu_reference()).  Prints ONE JSON line on rank 0.
 """
@@ -43,12 +56,10 @@ WORKLOADS = {
     # measure the HBM-bound kernels (filter, sweep, finalize, probabilities) against the HBM roofline
     "hbm": dict(n=20000, h=64, w=64, m=1, fs=40, stride=1),
 }
-# dram__bytes_read.sum + dram__bytes_write.sum of ONE gram_l2_s8_2cta_kernel launch at C2 from the committed
-# ncu capture (profiles/r01_launches_c2_final.summary.txt: 1699 MB read + 73 MB written; operands are 753 MB,
-# the 100 MB D1 mostly stays in L2)
-GRAM_DRAM_BYTES_C2 = 1.771e9
 METRIC = "frame-pairs/s (distance + temporal filter + converged future-cost)"
 L2_FLUSH_BYTES = 256 << 20
+NOMINAL_I8_TOPS = 4500.0            # dense int8 at the 1965 MHz boost clock
+TRAFFIC_FILE = os.path.join(ROOT, "profiles", "r02_gram_traffic.json")
 
 
 def workload_name(wl):
@@ -80,6 +91,7 @@ class ClockSampler:
 
     def __init__(self, index: int):
         self.samples, self.reasons, self.max_mhz, self._stop = [], set(), None, threading.Event()
+        self.power = []
         try:
             import pynvml
             pynvml.nvmlInit()
@@ -94,13 +106,14 @@ class ClockSampler:
         while not self._stop.is_set():
             try:
                 self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+                self.power.append(self.nv.nvmlDeviceGetPowerUsage(self.h) / 1e3)
                 r = self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
                 for bit, name in self.REASONS.items():
                     if r & bit:
                         self.reasons.add(name)
             except Exception:
                 pass
-            time.sleep(0.01)
+            time.sleep(0.005)
 
     def __enter__(self):
         if self.nv is not None:
@@ -116,25 +129,28 @@ class ClockSampler:
         if not self.samples:
             return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["unavailable"]}
         return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz,
-                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+                "reasons": sorted(self.reasons), "samples": len(self.samples),
+                "power_w_max": max(self.power) if self.power else None}
 
 
 # ------------------------------------------------------------------------------------ CPU reference arm
 def cpu_reference(wl, budget_s=20.0, D1_host=None, seed=0):
-    """The reference's own algorithm on the host cores (oracle port; kind = "port").
+    """The reference's own algorithm on the host cores (oracle port; kind = "port"), one bounded sample.
 
-    D1: the literal block algorithm of classic/computeD1.py:58-96 (repeat -> view -> torch.norm,
-    bs = 48) on as many 48x48 blocks as fit in ~budget_s, extrapolated to all ceil(N/48)^2 blocks
-    (each block costs the same).  D2 + future cost: in full on an N x N distance matrix (the GPU's D1
-    when given, else a synthetic symmetric one), with the row minima computed once per sweep — the
-    same arithmetic as the reference's O(M^3) loop, which could not finish at this size.
-    Returns dict(value=pairs/s, seconds=..., sample=...).
+    D1: the literal block algorithm of classic/computeD1.py:58-96 (repeat -> view -> torch.norm, bs = 48) on
+    as many 48x48 blocks as fit in ~0.6*budget_s; every block of the full clip costs the same, so the
+    sample's rate carries over.  D2 + future cost: in full on an N x N distance matrix (the GPU's D1 when
+    given, else a synthetic symmetric one) with the row minima computed once per sweep — the same arithmetic
+    as the reference's O(M^3) loop, which could not finish at this size; its time is charged to the sample
+    in proportion to the sampled pairs.  Returns dict(value = sampled pairs / their time, wall_s = what this
+    call really took, seconds_full = implied time of one full pass, ...).
     """
     from audio_video_textures_b200.synth import synth_video
     from oracle import classic as oc
     torch.set_num_threads(os.cpu_count())
     n, h, w, fs, stride = wl["n"], wl["h"], wl["w"], wl["fs"], wl["stride"]
     bs = 48
+    wall0 = time.perf_counter()
     sample_frames = synth_video(2 * bs, h, w, seed=seed).float()
     t0 = time.perf_counter()
     blocks = 0
@@ -143,9 +159,8 @@ def cpu_reference(wl, budget_s=20.0, D1_host=None, seed=0):
         blocks += done
         if time.perf_counter() - t0 > budget_s * 0.6 or blocks >= 64:
             break
-    t_block = (time.perf_counter() - t0) / blocks
+    t_blocks = time.perf_counter() - t0
     n_blocks = math.ceil(n / bs) ** 2
-    t_d1 = t_block * n_blocks
     if D1_host is None:
         g = torch.Generator().manual_seed(seed)
         a = torch.rand(n, n, generator=g) * 1000.0
@@ -155,11 +170,382 @@ def cpu_reference(wl, budget_s=20.0, D1_host=None, seed=0):
     D2 = oc.compute_D2(D1_host, f, fs, stride)[0]
     D3_new, trail = oc.future_cost(D2 ** 0.7)
     t_rest = time.perf_counter() - t1
-    total = t_d1 + t_rest
-    return dict(value=n * n / total, seconds=total, cores=os.cpu_count(), kind="port",
-                sample=(f"D1: {blocks} of {n_blocks} 48x48 blocks of the reference block algorithm timed "
-                        f"({t_block:.3f} s/block) and extrapolated ({t_d1:.0f} s); D2 + future cost "
-                        f"({len(trail)} sweeps, vectorised row-min) in full at M={D2.shape[0]}: {t_rest:.2f} s"))
+    frac = blocks / n_blocks                                  # share of the clip's pairs the sample covers
+    sample_pairs = frac * n * n
+    sample_s = t_blocks + t_rest * frac
+    return dict(value=sample_pairs / sample_s, seconds_full=sample_s / frac, wall_s=time.perf_counter() - wall0,
+                cores=os.cpu_count(), kind="port",
+                sample=(f"D1: {blocks} of {n_blocks} 48x48 blocks of the reference block algorithm "
+                        f"({t_blocks / blocks:.3f} s/block, every block costs the same) + the matching share of "
+                        f"D2 + future cost ({len(trail)} sweeps, vectorised row-min, run in full at M={D2.shape[0]}: "
+                        f"{t_rest:.2f} s); one full pass would take {sample_s / frac:.0f} s"))
+
+
+# ------------------------------------------------------------------------------------ helpers (GPU arm)
+def _events(n):
+    return [torch.cuda.Event(enable_timing=True) for _ in range(n)]
+
+
+def measure_i8_peak(dev):
+    """An int8 tensor-core peak measured on THIS box, two ways: cuBLASLt's int8 GEMM (torch._int_mm,
+    8192^3) and a long-K run of the repo's own Gram kernel (296 full 256x256 tiles = 4 per CTA pair,
+    K = 65536: the epilogue is 0.4 % of the tile time).  Best of 10 each, CUDA events."""
+    from audio_video_textures_b200 import engine
+    out = {}
+    try:
+        a = torch.randint(-128, 127, (8192, 8192), dtype=torch.int8, device=dev)
+        b = torch.randint(-128, 127, (8192, 8192), dtype=torch.int8, device=dev)
+        best = 1e9
+        for i in range(13):
+            ev = _events(2)
+            ev[0].record()
+            torch._int_mm(a, b)
+            ev[1].record()
+            torch.cuda.synchronize()
+            if i >= 3:
+                best = min(best, ev[0].elapsed_time(ev[1]))
+        out["cublaslt_int8_8192_tops"] = 2.0 * 8192 ** 3 / (best * 1e-3) / 1e12
+        del a, b
+    except Exception as exc:                                   # pragma: no cover - depends on the torch build
+        out["cublaslt_int8_8192_tops"] = None
+        out["cublaslt_note"] = f"torch._int_mm unavailable: {type(exc).__name__}"
+    n, k, rows = 9472, 65536, 2048
+    x = torch.randint(0, 255, (n, k), dtype=torch.uint8, device=dev)
+    pf = engine.pack_frames(x)
+    D = engine.empty_matrix(rows, n, dev)
+    job = [dict(row0=0, rows=rows, col0=0, cols=n, symmetric=0, count_stats=0, D=D.data_ptr(), d_row0=0,
+                ldd=D.stride(0))]
+    best = 1e9
+    for i in range(13):
+        ev = _events(2)
+        ev[0].record()
+        engine.gram_l2_jobs(pf, job)
+        ev[1].record()
+        torch.cuda.synchronize()
+        if i >= 3:
+            best = min(best, ev[0].elapsed_time(ev[1]))
+    out["own_kernel_longK_tops"] = 2.0 * rows * n * k / (best * 1e-3) / 1e12
+    out["own_kernel_longK_shape"] = f"{rows}x{n} outputs, K={k} (296 tiles of 256x256)"
+    del x, pf, D
+    vals = [v for v in (out["cublaslt_int8_8192_tops"], out["own_kernel_longK_tops"]) if v]
+    out["peak_tops"] = max(vals)
+    out["peak_source"] = ("cuBLASLt int8 8192^3" if out["peak_tops"] == out.get("cublaslt_int8_8192_tops")
+                          else "own kernel, long K")
+    return out
+
+
+def gram_roofline(frames, wl, gram_ms, step_share, dev, peaks):
+    """The tensor-bound kernel's line: executed and algorithmic int8 ops of ONE launch over its event-timed
+    duration, against the int8 peak measured here; in-kernel SM clock; DRAM traffic of the committed capture."""
+    from audio_video_textures_b200 import engine
+    n = wl["n"]
+    k = wl["h"] * wl["w"] * 3
+    kp = (k + 127) // 128 * 128
+    tiles_1d = math.ceil(n / 256)
+    tiles = tiles_1d * (tiles_1d + 1) // 2                                  # upper-triangle 256 x 256 tiles
+    executed = tiles * 256.0 * 256.0 * kp * 2.0
+    algorithmic = 2.0 * k * n * n
+    t = gram_ms * 1e-3
+    # SM clock inside the kernel: clock64 / globaltimer deltas of CTA 0's tile loop (median of 5 launches)
+    pf = engine.pack_frames(frames)
+    D1 = engine.empty_matrix(n, n, dev)
+    probe = torch.zeros(2, dtype=torch.int64, device=dev)
+    job = [dict(row0=0, rows=n, col0=0, cols=n, symmetric=1, count_stats=0, D=D1.data_ptr(), d_row0=0,
+                ldd=D1.stride(0), DT=D1.data_ptr(), dt_row0=0, ldt=D1.stride(0))]
+    mhz = []
+    for _ in range(5):
+        engine.gram_l2_jobs(pf, job, clock_probe=probe)
+        cyc, ns = (int(v) for v in probe.cpu())
+        if ns > 0:
+            mhz.append(1e3 * cyc / ns)
+    del D1
+    i8 = measure_i8_peak(dev)
+    traffic = None
+    traffic_note = "no committed capture for this workload"
+    if os.path.exists(TRAFFIC_FILE):
+        with open(TRAFFIC_FILE) as f:
+            tr = json.load(f)
+        if tr.get("workload") == workload_name(wl):
+            traffic = tr["dram_bytes_read"] + tr["dram_bytes_write"]
+            traffic_note = tr.get("source", "")
+    ex_tops = executed / t / 1e12
+    clk = float(np.median(mhz)) if mhz else None
+    return {
+        "kernel": "gram_l2_s8_2cta_kernel (tcgen05 kind::i8, cta_group::2, TMA-fed, symmetric tile schedule)",
+        "bound": "tensor", "unit": "TOP/s (int8)", "ms": gram_ms,
+        "achieved": ex_tops, "peak": i8["peak_tops"], "frac": ex_tops / i8["peak_tops"],
+        "peak_source": f"measured in this run: {i8['peak_source']}", "i8_peak_measurements": i8,
+        "executed_ops": executed, "algorithmic_ops": algorithmic, "algorithmic_tops": algorithmic / t / 1e12,
+        "tiles_executed": tiles, "tiles_full_matrix": tiles_1d * tiles_1d,
+        "sm_mhz_in_kernel": clk,
+        "frac_of_nominal_at_measured_clock": (ex_tops / (NOMINAL_I8_TOPS * clk / 1965.0)) if clk else None,
+        "frac_of_nominal_i8_4500": ex_tops / NOMINAL_I8_TOPS,
+        "bf16_peak_measured_tflops": peaks["bf16_tflops"],
+        "traffic": traffic, "traffic_source": traffic_note, "operand_bytes": float(n) * k,
+        "share_of_step": step_share,
+        "note": ("achieved = executed int8 ops (upper-triangle tiles, K padded to 128) / event-timed launch; peak = the "
+                 "larger of the two int8 rates measured in this run; algorithmic = 2*K*N^2 reported separately; "
+                 "sm_mhz_in_kernel = clock64/globaltimer inside the kernel (NVML's sampling cannot see a ~1 ms launch)")}
+
+
+def hbm_rooflines(dev, peaks):
+    """The HBM-bound kernels at M = 19961 (every matrix 1.6 GB): algorithmic bytes / event-timed launch against
+    the measured copy bandwidth.  L2 (126 MB) is irrelevant at this size; median of 5 launches each."""
+    from audio_video_textures_b200 import engine
+    from audio_video_textures_b200.synth import synth_video_cuda
+    wl = WORKLOADS["hbm"]
+    n, fs = wl["n"], wl["fs"]
+    k = wl["h"] * wl["w"] * 3
+    frames = synth_video_cuda(n, wl["h"], wl["w"], seed=1, device=dev)
+    out = []
+
+    def timed(fn, reps=5):
+        ms = []
+        for _ in range(reps + 1):
+            ev = _events(2)
+            ev[0].record()
+            r = fn()
+            ev[1].record()
+            torch.cuda.synchronize()
+            ms.append(ev[0].elapsed_time(ev[1]))
+        return float(np.median(ms[1:])), r
+
+    def line(kernel, nbytes, ms, what):
+        gbs = nbytes / (ms * 1e-3) / 1e9
+        out.append({"kernel": kernel, "bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                    "frac": gbs / peaks["hbm_gbs"], "ms": ms, "algorithmic_bytes": nbytes, "what": what})
+
+    ms, pf = timed(lambda: engine.pack_frames(frames))
+    line("frame_norms_u8_warp_kernel", float(n) * k, ms, f"K0: {n} rows of {k} B read once")
+    D1 = engine.gram_l2(pf)
+    m = engine.filtered_size(n, fs, 1)
+    ms, (D2, D3) = timed(lambda: engine.diag_filter(D1, fs, 1, p=0.7))
+    line("diag_filter_s1_kernel<40> (stride 1, smem sliding window)", 4.0 * n * n + 8.0 * m * m, ms,
+         f"K2 -m 1/2: read D1 {n}^2, write D2 + D3 {m}^2")
+    del D2
+    mv = torch.zeros((m + 31) // 32 * 32, dtype=torch.float32, device=dev)
+    out_m = torch.empty_like(mv)
+    import ctypes as C
+    from audio_video_textures_b200 import _lib
+
+    def sweep():
+        _lib.call("avtex_future_cost_sweep", _lib.ptr(D3), D3.stride(0), 0, m, m, _lib.ptr(mv), None,
+                  C.c_float(0.997), _lib.ptr(out_m), None, engine._dev(D3), engine._stream(D3))
+    ms, _ = timed(sweep)
+    line("future_cost_sweep_kernel", 4.0 * m * m, ms, f"K3: one sweep = one read of D3 {m}^2")
+    ms, D3n = timed(lambda: engine.future_cost_finalize(D3, mv[:m]))
+    line("future_cost_finalize_kernel", 8.0 * m * m, ms, "K4: read D3, write D3_new")
+    del D3
+    ms, _ = timed(lambda: engine.transition_probs(D3n, 3000.0, threshold=0.08, want_counts=True))
+    line("transition_probs_kernel<cache,1024>", 12.0 * m * m, ms, "K5: read D3_new once, write P3 and P3_new")
+    del D3n, D1
+    # stride-4 filter on the C5 row-shard shape (what one of 8 ranks runs at N = 100000): 12539 D1 rows x 100000
+    n5, rows5 = 100000, 12536 + 40
+    D1s = torch.empty((rows5, n5), dtype=torch.float32, device=dev).uniform_(1.0, 2.0)
+    m5 = engine.filtered_size(n5, fs, 4)
+    rows_out = (rows5 - fs) // 4 + 1
+    ms, _ = timed(lambda: engine.diag_filter(D1s, fs, 4, p=0.7, m=m5, a0=0, rows_out=rows_out, in_row0=0))
+    line("diag_filter_kernel<40,4,8> (stride 4, C5 shard)", 4.0 * rows5 * n5 + 8.0 * rows_out * m5, ms,
+         f"K2 -m 3: read {rows5} x {n5} D1 rows, write D2 + D3 {rows_out} x {m5}")
+    return out
+
+
+def synth_records(dev, state_c2):
+    """BASELINE.json metric, second half: synth frames/s.  Classic: the sampling walk over the survivor lists
+    (host loop, numpy legacy RNG; classic/video_textures.py:43-209).  Contrastive: the -e synthesis loop at the
+    embedding boundary for C3 / C4 (cvt/validate.py:324-572), 30 s of video at 30 fps."""
+    from audio_video_textures_b200 import engine
+    from audio_video_textures_b200.classic.video_textures import texture_walk
+    from audio_video_textures_b200.contrastive.validate import synthesize
+    from audio_video_textures_b200.synth import synth_audio_features, synth_embeddings
+    rec = {}
+    P3n, counts = state_c2["P3n"], state_c2["counts"]
+    t0 = time.perf_counter()
+    rowptr, colidx = engine.csr_from_matrix(P3n, counts)
+    csr_s = time.perf_counter() - t0
+    walks = {}
+    for mode in (3, 1):
+        np.random.seed(0)
+        t0 = time.perf_counter()
+        frames_list, jumps = texture_walk((rowptr, colidx), mode, 30, 30, 4, 40)
+        dt = time.perf_counter() - t0
+        walks[f"m{mode}"] = {"frames": len(frames_list), "frames_per_s": len(frames_list) / (dt + csr_s),
+                             "walk_ms": 1e3 * dt, "jump_count": int(jumps)}
+    rec["classic_walk_c2"] = {"survivor_csr_ms": 1e3 * csr_s, "nnz": int(rowptr[-1]), **walks,
+                              "note": "frames/s = emitted frames / (GPU survivor compaction + D2H + host walk); -nvl 30 at 30 fps"}
+    L, D = 20000, 2304
+    emb = synth_embeddings(L, D, seed=0, device=dev)
+    for name, A in (("c3", 0), ("c4_a128", 128), ("c4_a12288", 12288)):
+        kw = {}
+        if A:
+            kw = dict(alpha=0.5, q_audio=synth_audio_features(L, A, seed=0, device=dev),
+                      da_source=synth_audio_features(L, A, seed=1, device=dev),
+                      da_driving=synth_audio_features(160, A, seed=2, device=dev))
+        args = dict(temp=0.1, threshold=0.3, fps=30, new_video_length=30, window=15, stride=6)
+        np.random.seed(0)
+        synthesize(emb, **args, **kw)                                      # warm-up (tables, first launches)
+        torch.cuda.synchronize()
+        best = None
+        for rep in range(3):
+            np.random.seed(0)
+            t0 = time.perf_counter()
+            res = synthesize(emb, **args, **kw)
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            best = dt if best is None else min(best, dt)
+        steps = len(res["q_ids"])
+        # loop only: table normalisation excluded by timing the steps through a prepared state
+        from audio_video_textures_b200.contrastive.validate import SynthesisState
+        st = SynthesisState(emb, None, kw.get("q_audio"), None, kw.get("da_source"), kw.get("da_driving"))
+        torch.cuda.synchronize()
+        np.random.seed(0)
+        q, t0 = 10, time.perf_counter()
+        for it in range(1, steps + 1):
+            ch = st.step(q, it, 0.1, 0.5, 0.3)
+            q = int(np.random.choice(ch))
+        loop_s = time.perf_counter() - t0
+        row_bytes = 4.0 * L * (D + A) + (4.0 * L * A if A else 0.0)
+        rec[name] = {"config": f"contrastive synthesis -e -th 0.3 -temp 0.1{' -m 2 -alpha 0.5' if A else ''}: L={L} D={D} A={A}",
+                     "steps": steps, "frames": len(res["frame_ids"]), "ms_per_step": 1e3 * loop_s / steps,
+                     "frames_per_s": len(res["frame_ids"]) / loop_s, "window_pairs_per_s": steps * L / loop_s,
+                     "ms_per_step_incl_table_setup": 1e3 * best / steps,
+                     "hbm_bytes_per_step": row_bytes, "hbm_frac_of_step": row_bytes / (loop_s / steps) / 1e9 / load_peaks()["hbm_gbs"],
+                     "launches_per_step": st.launches_per_step}
+        del kw, st
+    return rec
+
+
+def c5_record(args, dev, rank, world, peaks):
+    """configs[4] at THIS N: 100000 frames 64x64, -m 3 -fs 40 -stride 4 (M = 24991).  Strong scaling: the same
+    clip at every N, rows sharded over the ranks (N = 1: the single-GPU path, D1 = 40 GB resident)."""
+    import torch.distributed as dist
+
+    from audio_video_textures_b200 import dist as avdist
+    from audio_video_textures_b200 import engine
+    from audio_video_textures_b200.synth import synth_video_cuda
+    wl = WORKLOADS["c5"]
+    n, fs, stride = wl["n"], wl["fs"], wl["stride"]
+    frames = synth_video_cuda(n, wl["h"], wl["w"], seed=0, device=dev)
+    flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
+    steps, warm = max(3, min(args.steps, 5)), 2
+    ws = avdist.SymmetricShardWorkspace(n, fs, stride, rank, world, dev) if world > 1 else None
+    stage_names = ["norms", "gram", "filter", "future_cost", "finalize"]
+
+    def one(timing):
+        if world == 1:
+            ev = _events(6)
+            ev[0].record()
+            pf = engine.pack_frames(frames)
+            ev[1].record()
+            D1 = engine.gram_l2(pf)
+            ev[2].record()
+            D2, D3 = engine.diag_filter(D1, fs, stride, p=0.7)
+            ev[3].record()
+            fc = engine.future_cost_fused(D3, 0.997)
+            ev[4].record()
+            D3n = engine.future_cost_finalize(D3, fc.mvec, 0.997)
+            ev[5].record()
+            torch.cuda.synchronize()
+            return ev[0].elapsed_time(ev[5]), {s: ev[i].elapsed_time(ev[i + 1]) for i, s in enumerate(stage_names)}, fc.n_sweeps
+        ev = _events(2)
+        ev[0].record()
+        res = avdist.classic_sharded(frames, fs, stride, rank, world, workspace=ws, timing=timing)
+        ev[1].record()
+        torch.cuda.synchronize()
+        return ev[0].elapsed_time(ev[1]), res.stage_ms, res.n_sweeps
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    for _ in range(warm):
+        one(False)
+    ms = []
+    for _ in range(steps):
+        flush.fill_(1)
+        sync_all()
+        ms.append(one(False)[0])
+    stage_runs = []
+    for _ in range(3):
+        flush.fill_(1)
+        sync_all()
+        _, st, sweeps = one(True)
+        stage_runs.append([st[s] for s in stage_names])
+    tot = torch.tensor([sum(ms)], dtype=torch.float64, device=dev)
+    stg = torch.tensor(np.median(np.array(stage_runs), axis=0), dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tot, op=dist.ReduceOp.MAX)
+        dist.all_reduce(stg, op=dist.ReduceOp.MAX)
+    # end to end: pinned host clip -> device (1/G per rank + NVLink all-gather) -> pipeline incl. sigma3 / P3_new ->
+    # survivor lists on the host
+    host = frames.reshape(n, -1).cpu().pin_memory()
+    del frames
+    e2e_ms, d2h = [], 0
+    for it in range(3):
+        flush.fill_(1)
+        sync_all()
+        t0 = time.perf_counter()
+        dev_frames = avdist.load_frames_sharded(host, rank, world, dev)
+        if world == 1:
+            pf = engine.pack_frames(dev_frames)
+            D1 = engine.gram_l2(pf)
+            D2, D3 = engine.diag_filter(D1, fs, stride, p=0.7)
+            fc = engine.future_cost_fused(D3, 0.997)
+            stats = engine.new_stats(dev)
+            D3n = engine.future_cost_finalize(D3, fc.mvec, 0.997, stats=stats)
+            sigma = engine.sigma_from_stats(*engine.read_stats(stats), 4.5)
+            P3, P3n, counts = engine.transition_probs(D3n, sigma, threshold=0.08, want_P=False, want_counts=True)
+            rowptr, colidx = engine.csr_from_matrix(P3n, counts)
+            del D1, D2, D3, D3n, P3n
+        else:
+            res = avdist.classic_sharded(dev_frames, fs, stride, rank, world, sigma_factor=4.5, threshold=0.08,
+                                         workspace=ws)
+            rowptr, colidx = avdist.gather_survivors(res)
+            del res
+        sync_all()
+        if it >= 1:
+            e2e_ms.append(1e3 * (time.perf_counter() - t0))
+        d2h = rowptr.nbytes + colidx.nbytes
+    t_e2e = torch.tensor([float(np.mean(e2e_ms))], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
+    step_ms = float(tot.item()) / steps
+    stages = {s: float(v) for s, v in zip(stage_names, stg.tolist())}
+    return {"workload": workload_name(wl), "n_gpus": world, "scaling": "strong", "steps": steps, "warmup": warm,
+            "ms_per_step": step_ms, "value": n * n / (step_ms * 1e-3), "unit": "frame-pairs/s",
+            "sweeps": int(sweeps), "M": engine.filtered_size(n, fs, stride),
+            "stages_ms_max_over_ranks": stages,
+            "e2e": {"ms_per_step": float(t_e2e.item()), "value": n * n / (float(t_e2e.item()) * 1e-3),
+                    "h2d_bytes_per_step": int(host.numel()), "d2h_bytes_per_step": int(d2h),
+                    "includes": "pinned host clip -> HBM, norms, Gram, filter, future cost, sigma3, P3_new, survivor CSR on the host"},
+            "l2": "256 MB L2 flush between timed steps"}
+
+
+def parity_record(dev, rank, world):
+    """Sharded == single-GPU on a 3000-frame clip (M = 741), through the same symmetric workspace path the timed
+    steps use; every rank checks its own shard; MIN over ranks."""
+    import torch.distributed as dist
+
+    from audio_video_textures_b200 import dist as avdist
+    from audio_video_textures_b200 import selfcheck
+    from audio_video_textures_b200.synth import synth_video
+    n, fs, stride = 3000, 40, 4
+    frames = synth_video(n, 32, 32, seed=3).to(dev)
+    ws = avdist.SymmetricShardWorkspace(n, fs, stride, rank, world, dev)
+    for _ in range(2):
+        res = avdist.classic_sharded(frames, fs, stride, rank, world, sigma_factor=4.5, threshold=0.08, workspace=ws)
+    single = selfcheck.single_gpu_pipeline(frames, fs, stride, 4.5, 0.08)
+    ok = selfcheck.shard_equals_single(res, single)
+    keys = sorted(ok)
+    flags = torch.tensor([int(ok[k]) for k in keys], device=dev)
+    dist.all_reduce(flags, op=dist.ReduceOp.MIN)
+    failed = [k for k, v in zip(keys, flags.tolist()) if not v]
+    return {"status": "bit-exact" if not failed else "MISMATCH: " + ",".join(failed),
+            "clip": f"{n} frames 32x32, -fs {fs} -stride {stride}, M={res.plan.m}", "ranks": world,
+            "checked": {"bit_exact": ["D1", "D2", "D3n", "sweeps", "survivors"], "rtol_1e-6": ["eps", "sigma"],
+                        "rtol_1e-5": ["P3"]},
+            "sweeps": int(res.n_sweeps)}
 
 
 # ------------------------------------------------------------------------------------ GPU arm
@@ -181,52 +567,44 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
     wl = scaled_workload(args.workload, world)
     n, fs, stride = wl["n"], wl["fs"], wl["stride"]
-    k = wl["h"] * wl["w"] * 3
     frames = synth_video_cuda(n, wl["h"], wl["w"], seed=0, device=dev)
     flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
     peaks = load_peaks()
     gram_ms, step_ms = [], []
     state = {}
-    workspace = peer_fc = None
+    workspace = None
     comm_note = ""
     if world > 1 and not args.no_symmetric:
         try:
             workspace = avdist.SymmetricShardWorkspace(n, fs, stride, rank, world, dev)
-            peer_fc = avdist.PeerFutureCost(avdist.plan_shards(n, fs, stride, world, rank).m, rank, world, dev)
             ok = torch.ones(1, device=dev)
         except Exception as exc:                      # no peer-mapped memory on this box: NCCL path of the same algorithm
-            workspace = peer_fc = None
+            workspace = None
             ok = torch.zeros(1, device=dev)
             comm_note = f"symmetric memory unavailable ({type(exc).__name__}): NCCL all-gather path"
         dist.all_reduce(ok, op=dist.ReduceOp.MIN)
         if int(ok.item()) == 0:
-            workspace = peer_fc = None
+            workspace = None
 
     def one_step(timed: bool):
-        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        ev = _events(4)
         ev[0].record()
-        pf = engine.pack_frames(frames) if world == 1 else avdist.pack_frames_sharded(frames, rank, world)
         if world == 1:
-            stats = engine.new_stats(dev)
+            pf = engine.pack_frames(frames)
             ev[1].record()
-            D1 = engine.gram_l2(pf, stats=stats)
+            D1 = engine.gram_l2(pf)
             ev[2].record()
             D2, D3 = engine.diag_filter(D1, fs, stride, p=0.7)
             fc = engine.future_cost_fused(D3, 0.997)
             D3n = engine.future_cost_finalize(D3, fc.mvec, 0.997)
             launches = 1 + 1 + 1 + 1 + 1
-            if not pf.exact_ok:
-                raise RuntimeError(pf.reason)
-            state.update(D1=D1, D3n=D3n, sweeps=fc.n_sweeps, m=D3.shape[0], rows=n)
+            state.update(D1=D1, D3n=D3n, fc=fc, m=D3.shape[0])
         else:
             ev[1].record()
-            res = avdist.classic_sharded(frames, fs, stride, rank, world, packed=pf, workspace=workspace,
-                                         peer_fc=peer_fc)
-            ev[2].record()       # (gram is the first kernel after ev[1]; the sharded call is timed as a whole)
+            res = avdist.classic_sharded(frames, fs, stride, rank, world, workspace=workspace)
+            ev[2].record()
             launches = res.launches
-            if res.stage_ms is not None and rank == 0 and timed:
-                print("stage_ms", {k: round(v, 3) for k, v in res.stage_ms.items()}, file=sys.stderr)
-            state.update(D3n=res.D3_new, sweeps=res.n_sweeps, m=res.plan.m, rows=res.plan.r_hi - res.plan.r_lo)
+            state.update(D3n=res.D3_new, fc=res.fc, m=res.plan.m)
         ev[3].record()
         torch.cuda.synchronize()
         if timed:
@@ -253,98 +631,131 @@ def run_ours(args):
             launches += one_step(True)
     sync_all()
     wall = time.perf_counter() - wall0
+    sweeps = int(state["fc"].n_sweeps)
     total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
     total_s = float(total_ms.item()) / 1e3
     value = n * n * args.steps / total_s
 
-    # ---- end to end through the reference-named entry points, host frames in pinned memory
-    e2e = None
+    # ---- per-stage times of the sharded step (max over ranks), measured on separate steps
+    stages = None
+    if world > 1:
+        names = ["norms", "gram", "filter", "future_cost", "finalize"]
+        runs = []
+        for _ in range(5):
+            flush.fill_(1)
+            sync_all()
+            res = avdist.classic_sharded(frames, fs, stride, rank, world, workspace=workspace, timing=True)
+            runs.append([res.stage_ms[s] for s in names])
+        stg = torch.tensor(np.median(np.array(runs), axis=0), dtype=torch.float64, device=dev)
+        dist.all_reduce(stg, op=dist.ReduceOp.MAX)
+        stages = {s: float(v) for s, v in zip(names, stg.tolist())}
+
+    # ---- end to end from pinned host frames; same scope at every N: ... sigma3, P3_new, survivor lists on the host
+    host = frames.reshape(n, -1).cpu().pin_memory()
+    f = torch.tensor(4.5, dtype=torch.float32)
+    times, d2h = [], 0
+    reps = args.warmup + max(3, args.steps // 4)
     if world == 1:
         from audio_video_textures_b200.classic.computeD1 import compute_D1
         from audio_video_textures_b200.classic.computeD2 import compute_D2
-        from audio_video_textures_b200.classic.q_learning import q_learning
-        host = frames.cpu().pin_memory()
-        f = torch.tensor(4.5, dtype=torch.float32)
-        times, d2h = [], 0
-        for it in range(args.warmup + max(3, args.steps // 4)):
+        from audio_video_textures_b200.classic.q_learning import LAST, q_learning
+        host4 = host.view(n, wl["h"], wl["w"], 3)
+        for it in range(reps):
             flush.fill_(1)
             torch.cuda.synchronize()
             t0 = time.perf_counter()
             with contextlib.redirect_stdout(io.StringIO()):
-                D1, P1, s1 = compute_D1(host, f, "RGB", slow=True, batch_size=48)
+                D1, P1, s1 = compute_D1(host4, f, "RGB", slow=True, batch_size=48)
                 if wl["m"] in (1, 2):
                     D2, P2, s2, _ = compute_D2(D1, f, filter_size=fs)
                 else:
                     D2, P2, s2, _ = compute_D2(D1, f, filter_size=fs, stride=stride)
                 D3n, P3, P3n, s3 = q_learning(D2, f, thresholding=0.08)
-            rowptr, colidx = engine.csr_from_matrix(P3n)            # what the walk consumes (D2H)
+            rowptr, colidx = engine.csr_from_matrix(P3n, LAST["counts"])          # what the walk consumes (D2H)
             sig = s3.item()
             torch.cuda.synchronize()
             if it >= args.warmup:
                 times.append(time.perf_counter() - t0)
             d2h = rowptr.nbytes + colidx.nbytes + 3 * 4
-        e2e = {"value": n * n / float(np.mean(times)), "unit": "frame-pairs/s",
-               "h2d_bytes_per_step": int(host.numel()), "d2h_bytes_per_step": int(d2h),
-               "ms_per_step": 1e3 * float(np.mean(times)),
-               "includes": "compute_D1+compute_D2+q_learning (P1,P2,P3,P3_new, sigmas) + survivor CSR D2H"}
-
-    elif world > 1:
-        # every rank copies the (replicated) clip from its own pinned host buffer, then runs its shard
-        host = frames.reshape(n, -1).cpu().pin_memory()
-        times = []
-        for it in range(args.warmup + max(3, args.steps // 4)):
+        state.update(P3n=P3n, counts=LAST["counts"])
+        t_e2e = float(np.mean(times))
+        includes = "compute_D1+compute_D2+q_learning (P1,P2,P3,P3_new, sigmas) + survivor CSR D2H"
+    else:
+        for it in range(reps):
             flush.fill_(1)
             sync_all()
             t0 = time.perf_counter()
             dev_frames = avdist.load_frames_sharded(host, rank, world, dev)     # 1/G over PCIe + NVLink all-gather
-            res = avdist.classic_sharded(dev_frames, fs, stride, rank, world, workspace=workspace, peer_fc=peer_fc)
+            res = avdist.classic_sharded(dev_frames, fs, stride, rank, world, sigma_factor=f, threshold=0.08,
+                                         workspace=workspace)
+            rowptr, colidx = avdist.gather_survivors(res)
             sync_all()
             if it >= args.warmup:
                 times.append(time.perf_counter() - t0)
+            d2h = rowptr.nbytes + colidx.nbytes + 4
         t = torch.tensor([float(np.mean(times))], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e = {"value": n * n / float(t.item()), "unit": "frame-pairs/s", "h2d_bytes_per_step": int(host.numel()),
-               "d2h_bytes_per_step": 8 * world, "ms_per_step": 1e3 * float(t.item()),
-               "includes": "each rank copies 1/G of the pinned host clip, NVLink all-gather replicates it, then the "
-                           "sharded distance/filter/future-cost; D3_new shards stay on device"}
+        t_e2e = float(t.item())
+        includes = ("each rank copies 1/G of the pinned host clip, NVLink all-gather replicates it; sharded norms / "
+                    "Gram / filter / future cost; sigma3 (all-reduce), P3, P3_new; survivor CSR gathered and copied to the host")
+    e2e = {"value": n * n / t_e2e, "unit": "frame-pairs/s", "h2d_bytes_per_step": int(host.numel()),
+           "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * t_e2e, "includes": includes}
+    del host
+
+    extra = {}
+    if world > 1 and workspace is not None and not args.skip_extra:
+        extra["parity"] = parity_record(dev, rank, world)
+    roof = hbm = cpu = None
+    if world == 1 and rank == 0:
+        g_ms = float(np.mean(gram_ms))
+        roof = gram_roofline(frames, wl, g_ms, g_ms * len(gram_ms) / sum(step_ms), dev, peaks)
+        if not args.skip_extra:
+            extra["synth"] = synth_records(dev, state)
+        D1_host = state["D1"].cpu() if n <= 8000 else None
+        state.clear()
+        if not args.skip_extra:
+            hbm = hbm_rooflines(dev, peaks)
+        cpu = {kk: vv for kk, vv in cpu_reference(wl, args.cpu_budget, D1_host).items() if kk != "wall_s"}
+        cpu["unit"] = "frame-pairs/s"
+    state.clear()
+    del frames
+    torch.cuda.empty_cache()
+    if not args.skip_extra and args.workload == "c2":
+        try:
+            extra["c5"] = c5_record(args, dev, rank, world, peaks)
+        except Exception as exc:                                            # never lose the main line to the extra record
+            extra["c5"] = {"error": f"{type(exc).__name__}: {exc}"}
 
     if rank != 0:
         return
-    m = state["m"]
     out = {
         "metric": METRIC, "value": value, "unit": "frame-pairs/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * total_s / args.steps, "higher_is_better": True,
         "scaling": "weak" if args.workload == "c2" else "strong", "vs_baseline": None,
         "dtype": "u8 (exact int32 tensor-core Gram) + fp32", "data": "synthetic",
         "config": {"workload": workload_name(wl), "name": args.workload,
-                   "detail": f"M={m}, {state['sweeps']} future-cost sweeps to eps <= 0.01",
+                   "detail": f"M={engine.filtered_size(n, fs, stride)}, {sweeps} future-cost sweeps to eps <= 0.01",
                    "l2": "256 MB L2 flush between timed steps",
                    "sharding": "single GPU" if world == 1 else
                    (f"rows over {world} ranks, N=5000*sqrt(G)" if args.workload == "c2" else f"rows over {world} ranks") +
-                   ("" if world == 1 or args.no_symmetric else "; symmetric Gram, transposed tiles pushed to peer shards over NVLink; future cost "
-                                                                 "fused with its all-gather (peer stores + flag barrier)")},
+                   ("" if args.no_symmetric or workspace is None else
+                    "; norms, transposed Gram tiles and per-sweep row minima pushed to peer shards over NVLink from inside the kernels")},
         "gpu_launches": launches, "wall_s": wall,
     }
-    if world == 1:
-        g_ms = float(np.mean(gram_ms))
-        flops = 2.0 * k * n * n
-        ach = flops / (g_ms * 1e-3) / 1e12
-        out["roofline"] = {
-            "kernel": "gram_l2_s8_2cta_kernel (tcgen05 kind::i8, cta_group::2, TMA-fed, symmetric tile schedule)", "bound": "tensor",
-            "achieved": ach, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": ach / peaks["bf16_tflops"],
-            "traffic": GRAM_DRAM_BYTES_C2 if args.workload == "c2" else None, "ms": g_ms,
-            "executed_tops": 0.5 * ach * (1.0 + 1.0 / math.ceil(n / 256)),     # upper-triangle 256x256 tiles only
-            "peak_i8_nominal_tops": 4500.0, "share_of_step": g_ms * len(gram_ms) / sum(step_ms),
-            "note": ("algorithmic flops 2*K*N^2 over the event-timed launch; the symmetric schedule executes "
-                     "~half of them and kind::i8 runs at twice the bf16 rate, so frac is quoted against the "
-                     f"measured bf16 peak from {peaks['source']} and can exceed 1")}
-        D1_host = state["D1"].cpu() if n <= 8000 else None
-        out["cpu_baseline"] = {kk: vv for kk, vv in cpu_reference(wl, args.cpu_budget, D1_host).items()
-                               if kk != "seconds"}
-        out["cpu_baseline"]["unit"] = "frame-pairs/s"
+    if roof is not None:
+        out["roofline"] = roof
+    if hbm is not None:
+        out["roofline_hbm"] = hbm
+    if cpu is not None:
+        out["cpu_baseline"] = cpu
+    if stages is not None:
+        out["stages"] = stages
     out["e2e"] = e2e
+    out["extra"] = extra
+    if "parity" in extra:
+        out["parity"] = extra["parity"]["status"]
     if comm_note:
         out["config"]["sharding"] += "; " + comm_note
     out["clocks"] = clocks.summary()
@@ -356,22 +767,28 @@ def run_reference(args):
     if rank != 0:
         return
     wl = scaled_workload(args.workload, args.gpus)        # the same clip the GPU arm uses at this --gpus
-    vals = []
+    total = args.warmup + args.steps
+    budget = min(args.cpu_budget, max(1.5, 150.0 / total))  # the whole run stays within a few minutes
+    vals, walls = [], []
     info = None
-    for it in range(args.warmup + args.steps):
-        info = cpu_reference(wl, budget_s=max(4.0, args.cpu_budget / max(1, args.steps)), seed=it)
+    for it in range(total):
+        info = cpu_reference(wl, budget_s=budget, seed=it)
         if it >= args.warmup:
             vals.append(info["value"])
+            walls.append(info["wall_s"])
     v = float(np.mean(vals))
-    k = wl["h"] * wl["w"] * 3
     out = {"impl": "reference", "metric": METRIC, "value": v, "unit": "frame-pairs/s", "n_gpus": args.gpus,
-           "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * wl["n"] ** 2 / v,
+           "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * float(np.mean(walls)),
            "higher_is_better": True, "scaling": "weak" if args.workload == "c2" else "strong", "vs_baseline": None,
            "dtype": "fp32", "data": "synthetic",
            "config": {"workload": workload_name(wl), "name": args.workload},
            "cpu_baseline": {"value": v, "unit": "frame-pairs/s", "cores": info["cores"], "kind": "port",
                             "sample": info["sample"]},
            "e2e": {"value": v, "unit": "frame-pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "full_pass_s": info["seconds_full"],
+           "note": ("each step times a bounded sample of the workload (ms_per_step is the sample's wall time); value = "
+                    "sampled frame-pairs / their time, which equals N^2 / full-pass time because every 48x48 block of "
+                    "the reference algorithm costs the same"),
            "gpu_launches": 0}
     print(json.dumps(out))
 
@@ -379,17 +796,16 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--no_symmetric", action="store_true",
-                    help="N>1: plain row shards (every rank computes its full row block) instead of peer pushes")
+                    help="N>1: plain row shards + NCCL exchange instead of peer pushes from the kernels")
+    ap.add_argument("--skip_extra", action="store_true", help="main line only (no c5 / synth / hbm / parity records)")
     ap.add_argument("--cpu_budget", type=float, default=20.0, help="seconds of CPU work for the baseline sample")
     args = ap.parse_args()
     if args.impl == "reference":
-        if args.warmup + args.steps > 6:          # keep the CPU arm within minutes
-            args.warmup, args.steps = min(args.warmup, 1), min(args.steps, 3)
         run_reference(args)
     else:
         run_ours(args)

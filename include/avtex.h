@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define AVTEX_ABI_VERSION 1
+#define AVTEX_ABI_VERSION 2
 #if defined(__GNUC__)
 #define AVTEX_API __attribute__((visibility("default")))
 #else
@@ -102,14 +102,25 @@ typedef struct AvtexGramJob {
     int64_t dt_row0, ldt;
     int symmetric, count_stats;
 } AvtexGramJob;
+/* clock_probe (nullable, 2 x u64 on the device): CTA 0 writes the SM cycles (clock64) and the wall nanoseconds
+ * (globaltimer) its first epilogue warp spent in the tile loop — their ratio is the SM clock the kernel really
+ * ran at, which NVML's millisecond-scale sampling cannot see for a ~1 ms kernel (bench.py reports it). */
 AVTEX_API int avtex_gram_l2_jobs(const void *operand, int operand_signed, int64_t n, int64_t k, int64_t ld,
                        const int64_t *sqnorm, const AvtexGramJob *h_jobs, int num_jobs, double *sum,
-                       unsigned long long *nnz, int device, void *stream);
+                       unsigned long long *nnz, unsigned long long *clock_probe, int device, void *stream);
 
 /* sqnorm[i] = sum_c frames[i,c]^2 (exact); max_centred (nullable, zeroed by the caller) receives
  * max_i sum_c (frames[i,c]-128)^2 via atomicMax.  HBM-bound: one read of the frames. */
 AVTEX_API int avtex_frame_norms_u8(const uint8_t *frames, int64_t n, int64_t k, int64_t ld, int64_t *sqnorm,
                          unsigned long long *max_centred, int device, void *stream);
+/* Row-sharded form: `frames` points at global row `row0` of the clip and holds n rows; the norm of row row0+i is
+ * written to h_sqnorm[d][row0 + i] for every destination d < num_dst (<= 8) and the centred maximum is raised in
+ * h_max_centred[d] (nullable array / entries).  The destinations are the SAME full-length vector on every GPU
+ * of the box (peer-mapped pointers, e.g. torch symmetric memory): each rank computes 1/G of the norms and pushes
+ * them to its peers from the kernel, replacing an all-gather + all-reduce pair per step (dist.py). */
+AVTEX_API int avtex_frame_norms_u8_push(const uint8_t *frames, int64_t n, int64_t k, int64_t ld, int64_t row0,
+                              int64_t *const *h_sqnorm, unsigned long long *const *h_max_centred, int num_dst,
+                              int device, void *stream);
 
 /* Same contract by direct difference in fp32 (the reference's own formula), for arbitrary float
  * features; SIMT, no tensor cores.  x is [n, k] fp32. */
@@ -141,6 +152,10 @@ AVTEX_API int avtex_diag_filter_pow(const float *D1, int64_t ld1, int64_t in_row
                           int stride, int64_t a0, int64_t rows_out, int64_t m,
                           float *D2, int64_t ld2, float *D3, int64_t ld3, float p,
                           double *sum, unsigned long long *nnz, int device, void *stream);
+/* out = D ** p elementwise (D >= 0, p > 0), same pow as the fused epilogue above.
+ * replaces: `D3 = D2 ** p` of classic/q_learning.py:34 when D2 is handed in by the caller. */
+AVTEX_API int avtex_pow_matrix(const float *D, int64_t ld, int64_t rows, int64_t cols, float p, float *out,
+                     int64_t ld_out, int device, void *stream);
 
 /* ---------------------------------------------------------------- K3/K4: future cost
  * One Jacobi sweep in vector form.  For the rows j in [row0, row0+rows) of D3
@@ -161,10 +176,11 @@ AVTEX_API int avtex_future_cost_sweep(const float *D3, int64_t ld, int64_t row0,
  * mbuf: 3 * mpad floats (mpad >= m, multiple of 4; scratch, rotated).  eps_trail: max_sweeps+1 doubles,
  * ZEROED by the caller; eps_trail[p] receives the numerator of sweep p.  info[0] = number of sweeps
  * (0 if max_sweeps was exhausted), info[1] = index (0..2) of the buffer in mbuf holding the vector m with
- * D3_new = D3 + fl(alpha*m).  replaces: classic/q_learning.py:39-51 including the while condition. */
+ * D3_new = D3 + fl(alpha*m); m_out (nullable, mpad floats) receives a copy of that vector, so the finalize kernel
+ * can be launched without a host read of info.  replaces: classic/q_learning.py:39-51 including the while condition. */
 AVTEX_API int avtex_future_cost_fused(const float *D3, int64_t ld, int64_t m, float alpha, float eps_stop,
                             int max_sweeps, float *mbuf, int64_t mpad, double *eps_trail, int *info,
-                            int device, void *stream);
+                            float *m_out, int device, void *stream);
 /* Row-sharded form of avtex_future_cost_fused (one cooperative kernel per GPU, launched on every rank):
  * this rank owns rows [row0, row0+rows) of D3.  After each sweep the kernel pushes its row minima into every
  * rank's m buffer and its eps numerator into every rank's slot array through PEER-MAPPED pointers
@@ -173,13 +189,17 @@ AVTEX_API int avtex_future_cost_fused(const float *D3, int64_t ld, int64_t m, fl
  * spins on the flag counters its peers write: the per-sweep all-gather and eps all-reduce happen inside the
  * kernel over NVLink.  Flags are monotonic: pass epoch_base = (calls so far) * (max_sweeps + 2), identical on
  * all ranks, and zero the flag/eps buffers once at allocation.  eps_local: [max_sweeps+1] doubles zeroed by
- * the caller (local scratch); eps_trail / info as in avtex_future_cost_fused; the result vector is
- * h_mbuf[rank] + info[1]*mpad.  world <= 8. */
+ * the caller (local scratch); eps_trail / info as in avtex_future_cost_fused (info: 4 ints, zeroed; info[2] = 1
+ * when a peer did not arrive within ~10 s — the kernel then returns on every rank instead of trapping); the
+ * result vector is h_mbuf[rank] + info[1]*mpad and is also copied to m_out (nullable, local, mpad floats).
+ * max_ctas != 0 caps the cooperative grid (> 0: that many CTAs; -G: 1/G of full occupancy): "virtual ranks" that
+ * share ONE device (tests) must all be resident at once for the flag barrier to close.  world <= 8. */
 AVTEX_API int avtex_future_cost_fused_peer(const float *D3, int64_t ld, int64_t row0, int64_t rows, int64_t m,
                                  float alpha, float eps_stop, int max_sweeps, int rank, int world,
                                  float *const *h_mbuf, int64_t mpad, double *const *h_epsbuf,
                                  unsigned int *const *h_flags, unsigned int epoch_base, double *eps_local,
-                                 double *eps_trail, int *info, int device, void *stream);
+                                 double *eps_trail, int *info, float *m_out, int max_ctas, int device,
+                                 void *stream);
 /* D3_new[j,:] = D3[j,:] + fl(alpha * mvec)  (j >= 1),  row 0 copied.  sum/nnz nullable.
  * replaces: the materialised D3_new of classic/q_learning.py:48 at convergence. */
 AVTEX_API int avtex_future_cost_finalize(const float *D3, int64_t ld, int64_t row0, int64_t rows, int64_t m,
@@ -224,6 +244,20 @@ AVTEX_API int avtex_cosine_scores(const float *tn, int64_t ld, int64_t rows, int
 AVTEX_API int avtex_select_step(const float *o, const float *a, int64_t L, int64_t q, float alpha,
                       float one_minus_alpha, float th, int *choices, int *n_choices, float *vals,
                       int device, void *stream);
+/* ONE launch per synthesis step (cooperative kernel): avtex_cosine_scores on the window table (and on the
+ * source-audio table against the driving row when sn/dn != NULL) fused with avtex_select_step — same arithmetic,
+ * same survivor list.  The list goes to choices / n_choices on the device AND, without a copy or a stream
+ * synchronisation, to MAPPED PINNED host memory: host_out = [seq, n, first host_cap survivors]; the sequence
+ * word `seq` is written last (after __threadfence_system), the host polls it.  Workspaces (device): ws_f32
+ * 3*L floats; ws_acc 8 doubles and ws_max 2 uint32, ZEROED once before the first step (the kernel re-arms the
+ * other parity itself; seq must increase by 1 per call); ws_counts >= 4 * #SM ints.
+ * replaces: cvt/models/models.py:351-352,412-417,433-457 + cvt/validate.py:369-378,524-527,554,558,568 per step. */
+AVTEX_API int avtex_synthesis_step(const float *tn, int64_t ld, int64_t L, int64_t dim, const float *qn,
+                         const float *sn, int64_t lds, int64_t dimA, const float *dn, float temp,
+                         int64_t q, float alpha, float one_minus_alpha, float th, float *ws_f32,
+                         double *ws_acc, unsigned int *ws_max, int *ws_counts, int ws_counts_len,
+                         int *choices, int *n_choices, float *vals, int *host_out, int host_cap,
+                         int seq, int device, void *stream);
 /* out[0] = arg max_w <normalize(x[w,:]), normalize(d)> with strict '>' against a running max that
  * starts at 0 (first maximum wins; 0 if no similarity is positive).
  * replaces: the start-segment search of cvt/validate.py:222-240. */

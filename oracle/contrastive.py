@@ -147,6 +147,8 @@ def synthesize(t_emb, temp, threshold, mbs, fps, new_video_length, window, strid
     L = t_emb.shape[0]
     W, S = window, stride
     max_length = math.ceil(fps) * new_video_length
+    if da_driving is not None:                                      # validate.py:260-263
+        max_length = min(max_length, np.ceil(fps) * np.floor(len(da_driving) * S + W))
     if q_audio is not None:
         max_a = q_audio.shape[0] - 1
         a_idx = [min(i, max_a) for i in range(L)]

@@ -8,7 +8,7 @@ import torch.distributed as dist
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from audio_video_textures_b200 import dist as avd  # noqa: E402
-from audio_video_textures_b200 import engine  # noqa: E402
+from audio_video_textures_b200 import engine, selfcheck  # noqa: E402
 from audio_video_textures_b200.classic.video_textures import texture_walk  # noqa: E402
 from audio_video_textures_b200.synth import synth_video  # noqa: E402
 
@@ -22,32 +22,15 @@ def main():
     frames = synth_video(n, h, w, seed=2).cuda()
     mode = sys.argv[6] if len(sys.argv) > 6 else "rows"
     ws = avd.SymmetricShardWorkspace(n, fs, stride, rank, world, frames.device) if mode == "sym" else None
-    pfc = avd.PeerFutureCost(avd.plan_shards(n, fs, stride, world, rank).m, rank, world, frames.device) \
-        if mode == "sym" else None
-    for _ in range(3 if mode == "sym" else 1):          # repeated calls reuse the symmetric buffers (flag epochs)
-        res = avd.classic_sharded(frames, fs, stride, rank, world, sigma_factor=f, threshold=th, workspace=ws,
-                                  peer_fc=pfc)
+    for _ in range(3 if mode == "sym" else 1):          # repeated calls reuse the symmetric buffers (parities, flag epochs)
+        res = avd.classic_sharded(frames, fs, stride, rank, world, sigma_factor=f, threshold=th, workspace=ws)
     rowptr, colidx = avd.gather_survivors(res)
-    # single-GPU result on every rank
-    pf = engine.pack_frames(frames)
+    single = selfcheck.single_gpu_pipeline(frames, fs, stride, f, th)
     pfs = avd.pack_frames_sharded(frames, rank, world)
-    assert torch.equal(pfs.sqnorm, pf.sqnorm) and pfs.exact_ok == pf.exact_ok
-    D1 = engine.gram_l2(pf)
-    D2, D3 = engine.diag_filter(D1, fs, stride, p=0.7)
-    fc = engine.future_cost(D3)
-    stats = engine.new_stats(frames.device)
-    D3n = engine.future_cost_finalize(D3, fc.mvec, stats=stats)
-    sigma = engine.sigma_from_stats(*engine.read_stats(stats), f)
-    P3, P3n, counts = engine.transition_probs(D3n, sigma, threshold=th, want_counts=True)
-    rp1, ci1 = engine.csr_from_matrix(P3n, counts)
-    p = res.plan
-    own = p.a1 - p.a0
-    ok = dict(
-        D1=torch.equal(res.D1, D1[p.r_lo:p.r_hi]), D2=torch.equal(res.D2, D2[p.a0:p.a1h]),
-        D3n=torch.equal(res.D3_new, D3n[p.a0:p.a1h]), sweeps=res.n_sweeps == fc.n_sweeps,
-        sigma=abs(float(res.sigma) - float(sigma)) <= 1e-6 * float(sigma),
-        P3=torch.allclose(res.P3, P3[p.a0:p.a1], rtol=1e-5, atol=0),
-        csr=np.array_equal(rowptr, rp1) and np.array_equal(colidx, ci1))
+    assert torch.equal(pfs.sqnorm, single["pf"].sqnorm) and pfs.exact_ok == single["pf"].exact_ok
+    ok = selfcheck.shard_equals_single(res, single)
+    rp1, ci1 = engine.csr_from_matrix(single["P3n"], single["counts"])
+    ok["csr"] = np.array_equal(rowptr, rp1) and np.array_equal(colidx, ci1)
     np.random.seed(0)
     a = texture_walk((rowptr, colidx), 1, 30, 5, stride, fs)
     np.random.seed(0)
@@ -55,6 +38,7 @@ def main():
     ok["walk"] = a == b
     flag = torch.tensor([int(all(ok.values()))], device="cuda")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    p = res.plan
     if rank == 0:
         print("DIST_CHECK", "PASS" if int(flag) == 1 else "FAIL", mode, ok, "world", world, "M", p.m, "sweeps", res.n_sweeps)
     else:

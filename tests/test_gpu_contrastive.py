@@ -79,6 +79,40 @@ def test_select_step_matches_oracle(eng, L, q, audio):
     np.testing.assert_allclose(vals.cpu()[ids].numpy(), out.numpy(), rtol=1e-5, atol=0)
 
 
+@pytest.mark.parametrize("L,D,A,q", [(96, 64, 0, 10), (96, 64, 32, 95), (5000, 256, 0, 1234), (5000, 256, 128, 0),
+                                     (1025, 100, 0, 1024), (2, 8, 0, 1), (3000, 2304, 128, 77)])
+def test_fused_synthesis_step_equals_separate_kernels(eng, L, D, A, q):
+    """avtex_synthesis_step (one cooperative launch, result in mapped pinned memory) == avtex_cosine_scores +
+    avtex_select_step: same logits bit for bit, same survivor list, same renormalised values; repeated calls
+    alternate the accumulator parity; a survivor list longer than the pinned window falls back to a D2H copy."""
+    from audio_video_textures_b200.synth import synth_audio_features, synth_embeddings
+    tn = eng.l2_normalize_rows(synth_embeddings(L, D, seed=L + q).cuda())
+    sn = dn = None
+    if A:
+        sn = eng.l2_normalize_rows(synth_audio_features(L, A, seed=1).cuda())
+        dn = eng.l2_normalize_rows(synth_audio_features(4, A, seed=2).cuda())
+    th, alpha, temp = 0.3, 0.5, 0.1
+    o = eng.cosine_scores(tn, tn[q], temp)
+    a = eng.cosine_scores(sn, dn[1], temp) if A else None
+    sel = torch.zeros(L + 1, dtype=torch.int32, device="cuda")
+    vals = torch.zeros(L, device="cuda")
+    eng.select_step(o, a, q, alpha, th, sel[1:], sel[:1], vals)
+    want = sel[1:int(sel[0]) + 1].cpu().numpy()
+    for cap in (4096, 3):
+        ws = eng.SynthesisWorkspace(L, "cuda", host_cap=cap)
+        v2 = torch.zeros(L, device="cuda")
+        for rep in range(3):                                   # parity 1, 0, 1
+            got = eng.synthesis_step(ws, tn, tn[q], q, temp, alpha, th, sn, dn[1] if A else None, v2)
+            np.testing.assert_array_equal(got, want)
+        assert torch.equal(ws.f32[:L], o)
+        if A:
+            assert torch.equal(ws.f32[L:2 * L], a)
+        mask = torch.ones(L, dtype=torch.bool)
+        if q != L - 1:
+            mask[q] = False
+        assert torch.equal(v2.cpu()[mask], vals.cpu()[mask])
+
+
 def test_synthesis_sequences_bit_exact(eng):
     from audio_video_textures_b200.contrastive.validate import start_segment, synthesize
     g = load_golden("contrastive_small")
@@ -116,6 +150,51 @@ def test_synthesis_medium_against_oracle(eng):
                      q_start=10)
     assert got["q_ids"] == want["q_ids"] and got["frame_ids"] == want["frame_ids"]
     assert got["jump_count"] == want["jump_count"] and got["nz_counts"] == want["nz_counts"]
+
+
+def _full_size_case(A, nvl, seed):
+    """BASELINE configs[2]/[3] at full size (L = 20000 windows, D = 2304 [+ A audio dims]) against
+    oracle.contrastive.synthesize on the same tables: chosen windows, emitted frames, survivor counts and jump
+    count bit-exact under one numpy seed; the oracle's minimum threshold margin is printed.
+    Reference: cvt/models/models.py:351-352,412-457; cvt/validate.py:369-378,524-572."""
+    from audio_video_textures_b200.contrastive.validate import synthesize
+    from audio_video_textures_b200.synth import synth_audio_features, synth_embeddings
+    from oracle import contrastive as oc
+    L, D = 20000, 2304
+    emb = synth_embeddings(L, D, seed=0, device="cuda")
+    kw, cpu_kw = {}, {}
+    if A:
+        qa = synth_audio_features(L, A, seed=0, device="cuda")
+        das = synth_audio_features(L, A, seed=1, device="cuda")
+        dad = synth_audio_features(160, A, seed=2, device="cuda")
+        kw = dict(alpha=0.5, q_audio=qa, da_source=das, da_driving=dad)
+        cpu_kw = dict(alpha=0.5, q_audio=qa.cpu(), da_source=das.cpu(), da_driving=dad.cpu())
+    np.random.seed(seed)
+    got = synthesize(emb, temp=0.1, threshold=0.3, fps=30, new_video_length=nvl, window=15, stride=6, **kw)
+    np.random.seed(seed)
+    want = oc.synthesize(emb.cpu(), 0.1, 0.3, 150, 30, nvl, 15, 6, q_start=got["start"], return_debug=True, **cpu_kw)
+    print(f"L={L} D={D} A={A}: {len(want['q_ids'])} steps, oracle min threshold margin {min(want['margins']):.3e}, "
+          f"mean survivors {np.mean(want['nz_counts']):.1f}, jumps {want['jump_count']}")
+    if min(want["margins"]) < 1e-5:
+        pytest.skip("fixture too close to the threshold cut")
+    assert got["q_ids"] == want["q_ids"] and got["frame_ids"] == want["frame_ids"]
+    assert got["nz_counts"] == want["nz_counts"] and got["jump_count"] == want["jump_count"]
+    return got
+
+
+def test_c3_full_size_synthesis_matches_oracle(eng):
+    got = _full_size_case(A=0, nvl=30, seed=5)           # -e -th 0.3 -temp 0.1, 30 s at 30 fps: 150 steps
+    assert len(got["q_ids"]) >= 148
+
+
+def test_c4_full_size_audio_conditioned_a128(eng):
+    got = _full_size_case(A=128, nvl=30, seed=6)         # -m 2 -alpha 0.5, canonical 128-d VGGish: 150 steps
+    assert len(got["q_ids"]) >= 148
+
+
+def test_c4_full_size_audio_conditioned_a12288(eng):
+    got = _full_size_case(A=12288, nvl=8, seed=7)        # reference-faithful 12288-d conv map: 39 steps (CPU time)
+    assert len(got["q_ids"]) >= 38
 
 
 def test_cli_main_synthesis_mode(eng, capsys):

@@ -81,3 +81,67 @@ def test_c2_filter_future_cost_probabilities_properties(c2):
     # threshold monotone: a larger threshold keeps a superset
     _, P3n_wide, _ = eng.transition_probs(D3n, sigma, threshold=0.2)
     assert bool(((P3n != 0) <= (P3n_wide != 0)).all())
+
+
+def test_c2_pipeline_matches_oracle(c2):
+    """BASELINE configs[1] at full size against the CPU oracle: the GPU D1 (5000 x 5000, exact integer Gram,
+    checked above) is handed to oracle.classic.compute_D2 / q_learning (0.05 s on the host at M = 1241) and every
+    downstream quantity of the drop-in entry points is compared: D2, sigma2, P2, eps trail + sweep count, D3_new,
+    sigma3, P3 to rtol 1e-4 (stated tolerance), the survivor CSR of P3_new and the -m 1/2/3 walks bit for bit.
+    Reference: classic/computeD2.py:21-52, classic/q_learning.py:27-68, classic/video_textures.py:43-209."""
+    import contextlib
+    import io
+
+    from audio_video_textures_b200.classic.computeD2 import compute_D2
+    from audio_video_textures_b200.classic.q_learning import LAST, q_learning
+    from audio_video_textures_b200.classic.video_textures import texture_walk
+    from oracle import classic as oc
+    eng, frames, pf, D1, stats = c2
+    fs, stride, th = 40, 4, 0.08
+    f = torch.tensor(4.5, dtype=torch.float32)
+    D1h = D1.cpu().contiguous()
+    D2o, P2o, s2o, _ = oc.compute_D2(D1h, f, fs, stride)
+    D3o, P3o, P3no, s3o, trail = oc.q_learning(D2o, f, thresholding=th, return_trail=True)
+    buf = io.StringIO()
+    with contextlib.redirect_stdout(buf):
+        D2, P2, s2, bf = compute_D2(D1, f, filter_size=fs, stride=stride)
+        D3n, P3, P3n, s3 = q_learning(D2, f, thresholding=th)
+    assert buf.getvalue().count("Eps:") == len(trail)              # one printed line per reference sweep
+    rt = dict(rtol=1e-4, atol=0)
+    np.testing.assert_allclose(D2.cpu().numpy(), D2o.numpy(), **rt)
+    np.testing.assert_allclose(float(s2), float(s2o), rtol=1e-5)
+    np.testing.assert_allclose(P2.cpu().numpy(), P2o.numpy(), rtol=1e-4, atol=1e-30)
+    assert LAST["n_sweeps"] == len(trail)
+    np.testing.assert_allclose(LAST["eps_trail"], trail, rtol=1e-4, atol=1e-6)
+    assert all(abs(e - 0.01) / 0.01 > 1e-3 for e in trail), "stop rule marginal for this fixture"
+    np.testing.assert_allclose(D3n.cpu().numpy(), D3o.numpy(), **rt)
+    np.testing.assert_allclose(float(s3), float(s3o), rtol=1e-5)
+    np.testing.assert_allclose(P3.cpu().numpy(), P3o.numpy(), rtol=1e-4, atol=1e-30)
+    # survivor sets: elements within the value tolerance of their row's cut may legitimately flip; everything
+    # else must agree exactly
+    mx = P3o.max(dim=1, keepdim=True)[0]
+    cut = mx - np.float32(th) * mx
+    rel = ((P3o - cut).abs() / cut)
+    got_nz, want_nz = (P3n.cpu() != 0), (P3no != 0)
+    diff = got_nz != want_nz
+    margin = float(rel.min())
+    print(f"C2 threshold margin (min over all {P3o.numel()} elements): {margin:.3e}; "
+          f"survivor mismatches: {int(diff.sum())}; sweeps {len(trail)}; eps trail {[round(e, 4) for e in trail]}")
+    assert bool((rel[diff] < 1e-5).all()), "survivor sets differ away from the threshold cut"
+    clean_rows = ~diff.any(dim=1)
+    rowptr, cols = eng.csr_from_matrix(P3n, LAST["counts"])
+    for i in torch.nonzero(clean_rows).view(-1).tolist()[::17]:
+        np.testing.assert_array_equal(cols[rowptr[i]:rowptr[i + 1]], torch.nonzero(want_nz[i]).view(-1).numpy())
+    # the walks (900 frames = fps 30 x nvl 30): bit-exact whenever every visited row is clean
+    for mode in (3, 1, 2):
+        np.random.seed(0)
+        want, wj = oc.walk(P3no, mode, 30, 30, stride, fs)
+        np.random.seed(0)
+        got, gj = texture_walk((rowptr, cols), mode, 30, 30, stride, fs)
+        if int(diff.sum()) == 0:
+            assert got == want and gj == wj, f"-m {mode} walk differs"
+        else:                                                      # only rows off the (rare) flipped ones are comparable
+            visited = set(want) if mode == 1 else None
+            if visited is not None and not any(bool(diff[v].any()) for v in visited if v < diff.shape[0]):
+                assert got == want and gj == wj, f"-m {mode} walk differs"
+    assert len(got) >= 900

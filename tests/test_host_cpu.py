@@ -153,51 +153,57 @@ def test_shard_plan_covers_rows_and_halos(n, fs, stride, world):
     assert owned == list(range(m))
 
 
-@pytest.mark.parametrize("n,fs,stride,world", [(7072, 40, 4, 2), (12000, 40, 4, 8), (2051, 40, 4, 3), (333, 16, 1, 2)])
+@pytest.mark.parametrize("n,fs,stride,world", [(7072, 40, 4, 2), (12000, 40, 4, 8), (2051, 40, 4, 3), (333, 16, 1, 2),
+                                               (300, 40, 1, 8), (100000, 40, 4, 8)])
 def test_symmetric_shard_jobs_cover_every_needed_element_once(n, fs, stride, world):
     """Host logic of the peer-push scheme (no GPU, no process group): over all ranks, the direct and the
-    transposed destinations of the job lists cover every (row, col) of every rank's D1 shard exactly once."""
+    transposed destinations of the job lists cover every (row, col) of every rank's CORE rows exactly once, and
+    the halo pieces come from the owners' core rows only (also when shard*stride < fs: (300, 40, 1, 8))."""
     from audio_video_textures_b200 import dist as avd
-
-    class _WS(avd.SymmetricShardWorkspace):
-        def __init__(self, rank):                           # geometry only: no symmetric-memory allocation
-            self.n, self.fs, self.stride, self.rank, self.world = n, fs, stride, rank, world
-            self.plans = [avd.plan_shards(n, fs, stride, world, r) for r in range(world)]
-            self.plan = self.plans[rank]
-            self.ld = (n + 31) // 32 * 32
-            self.ptrs = [1000 + r for r in range(world)]     # stand-in "pointers" = rank ids
-
     plans = [avd.plan_shards(n, fs, stride, world, r) for r in range(world)]
-    cover = [np.zeros((p.r_hi - p.r_lo, n), dtype=np.int16) for p in plans]
+    ld = (n + 31) // 32 * 32
+    ptrs = [1000 + r for r in range(world)]                  # stand-in "pointers" = rank ids
+    big = n > 20000                                          # 100k: interval bookkeeping only (no n x n cover arrays)
+    cover = None if big else [np.zeros((p.r_hi - p.r_lo, n), dtype=np.int16) for p in plans]
     work = []
     for r in range(world):
-        jobs = _WS(r).jobs()
+        jobs = avd.symmetric_jobs(plans, r, ptrs, ld, stride)
         assert len(jobs) <= 16
         pairs = 0
         for j in jobs:
             rs, cs = slice(j["row0"], j["row0"] + j["rows"]), slice(j["col0"], j["col0"] + j["cols"])
+            assert j["ldd"] == ld and j["ldt"] == ld
             tri = None
             if j["symmetric"]:
                 assert j["row0"] == j["col0"] and j["rows"] == j["cols"]
-                tri = np.triu(np.ones((j["rows"], j["cols"]), dtype=np.int16))
-            if j.get("D") is not None:
-                owner = j["D"] - 1000
-                assert owner == r
-                blk = cover[owner][rs.start - j["d_row0"]: rs.stop - j["d_row0"], cs]
+                tri = None if big else np.triu(np.ones((j["rows"], j["cols"]), dtype=np.int16))
+            owner_d, owner_t = j["D"] - 1000, j["DT"] - 1000
+            assert owner_d == r
+            lo_t, hi_t = avd.core_rows(plans, owner_t, stride)
+            assert lo_t <= cs.start and cs.stop <= hi_t        # pushes land in the destination's CORE rows only
+            if not big:
+                blk = cover[owner_d][rs.start - j["d_row0"]: rs.stop - j["d_row0"], cs]
                 blk += 1 if tri is None else tri
-            if j.get("DT") is not None:
-                owner = j["DT"] - 1000
-                blk = cover[owner][cs.start - j["dt_row0"]: cs.stop - j["dt_row0"], rs]
+                blk = cover[owner_t][cs.start - j["dt_row0"]: cs.stop - j["dt_row0"], rs]
                 blk += 1 if tri is None else (np.triu(np.ones((j["rows"], j["cols"]), dtype=np.int16), 1)).T
             pairs += j["rows"] * j["cols"] // (2 if j["symmetric"] else 1)
         work.append(pairs)
-    for r, c in enumerate(cover):                            # halo rows arrive by a peer copy of the next rank's first rows
-        ws = _WS(r)
-        core_rows = ws.core(r)[1] - plans[r].r_lo
-        assert c[:core_rows].min() == 1 and c[:core_rows].max() == 1
-        assert ws.halo_rows() == c.shape[0] - core_rows and (c[core_rows:] == 0).all()
+    for r in range(world):
+        lo, hi = avd.core_rows(plans, r, stride)
+        core = hi - plans[r].r_lo
+        if not big:
+            c = cover[r]
+            assert c[:core].min() == 1 and c[:core].max() == 1 and (c[core:] == 0).all()
+        # halo: contiguous pieces that start where the core ends, each inside its owner's core
+        need = hi
+        for owner, row, rows in avd.halo_sources(plans, r, stride):
+            olo, ohi = avd.core_rows(plans, owner, stride)
+            assert owner > r and row == need and olo <= row and row + rows <= ohi
+            need += rows
+        assert need == plans[r].r_hi
         if r + 1 < world:
-            assert plans[r + 1].r_lo == ws.core(r)[1] and ws.halo_rows() <= ws.core(r + 1)[1] - ws.core(r + 1)[0]
+            assert plans[r + 1].r_lo == hi
+    assert sum(work) >= n * n // 2 - n                                    # nothing is left uncomputed
     assert max(work) <= 1.25 * (n * n / (2 * world)) + 300 * n           # balanced up to halos and tile rounding
 
 
