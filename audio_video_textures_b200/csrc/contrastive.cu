@@ -17,6 +17,7 @@ namespace cg = cooperative_groups;
 namespace {
 
 constexpr int NT = 256;
+constexpr int SELT = 1024;
 
 __global__ void __launch_bounds__(NT)
 l2_normalize_rows_kernel(const float *__restrict__ x, int64_t ld, int64_t dim, float *__restrict__ y,
@@ -76,8 +77,6 @@ cosine_scores_kernel(const float *__restrict__ tn, int64_t ld, int64_t rows, int
     const float dot = warp_sum((acc0 + acc1) + (acc2 + acc3));
     if (lane == 0) out[w] = __fdiv_rn(dot, temp);
 }
-
-constexpr int SELT = 1024;
 
 __global__ void __launch_bounds__(SELT)
 select_step_kernel(const float *__restrict__ o, const float *__restrict__ a, int64_t L, int64_t q,
@@ -159,11 +158,13 @@ select_step_kernel(const float *__restrict__ o, const float *__restrict__ a, int
 }
 
 // ------------------------------------------------------------------ one launch per synthesis step
-// K6 + K7 fused (cooperative kernel): scores of the query against all L windows (+ the driving-audio scores),
-// the plain sums, alpha-mix, max, threshold, survivor sum and the ORDERED survivor list, with three grid
-// barriers instead of three launches, a device-to-host copy and a stream synchronisation per step
-// (round 1: 0.10 ms per step for a 39 us GEMV).  The count and the first `host_cap` survivors are written
-// straight into MAPPED PINNED host memory, followed by the step's sequence number: the host polls that word.
+// K6 + K7 fused: scores of the query against all L windows (+ the driving-audio scores) and their plain sums by
+// all CTAs (rows handed out dynamically); the LAST CTA to finish (atomic ticket) does the alpha-mix, max,
+// threshold, survivor sum and the ORDERED survivor list — one ordinary launch, no grid barrier, instead of three
+// launches, a device-to-host copy and a stream synchronisation per step (round 1: 0.10 ms per step for a 39 us
+// GEMV; a first cooperative version with three grid barriers still took 0.08 ms).  The count and the first
+// `host_cap` survivors are written straight into MAPPED PINNED host memory, followed by the step's sequence
+// number: the host polls that word.
 // Same arithmetic as cosine_scores_kernel + select_step_kernel (explicit roundings, fp64 sums cast to fp32), so
 // the survivor lists stay bit-identical to the reference restatement (cvt/validate.py:524-527,554,558,568).
 struct SynthStepArgs {
@@ -175,21 +176,13 @@ struct SynthStepArgs {
     int64_t q;
     float *o, *a, *v;                              // [L] scratch: logits, audio logits, mixed values
     double *acc;                                   // [2][4] by step parity: sum o, sum a, sum kept, (unused)
-    unsigned int *mx;                              // [2] ordered-int encoded maximum, by step parity
-    int *counts;                                   // [gridDim.x] survivors per CTA segment
+    unsigned int *mx;                              // [2][2] by step parity: dynamic row counter, CTA ticket
+    int *counts;                                   // (unused)
     int *choices, *n_choices;                      // device copy of the survivor list
     float *vals;                                   // nullable [L]
     volatile int *host;                            // mapped pinned: [seq, n, choices[0..host_cap)]
     int host_cap, seq, parity;
 };
-
-__device__ __forceinline__ unsigned int order_bits(float f) {          // monotone float -> uint
-    const unsigned int u = __float_as_uint(f);
-    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
-}
-__device__ __forceinline__ float unorder_bits(unsigned int u) {
-    return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
-}
 
 __device__ __forceinline__ float warp_row_dot(const float *__restrict__ row, const float *__restrict__ qn, int64_t dim,
                                               int lane) {
@@ -225,28 +218,112 @@ __device__ __forceinline__ float warp_row_dot(const float *__restrict__ row, con
     return warp_sum((acc0 + acc1) + (acc2 + acc3));
 }
 
-__global__ void __launch_bounds__(NT)
-synthesis_step_kernel(const SynthStepArgs p) {
+// Selection over the L logits by ONE CTA of SELT threads (the last CTA of the step to finish its rows):
+// mixed values + max, survivor sum, ordered compaction.  Each warp owns a contiguous slice of windows, so the
+// ordered compaction needs one prefix over 32 warp counts instead of a barrier per 1024 elements.
+__device__ void synthesis_select(const SynthStepArgs &p, double *acc) {
     __shared__ double dred[32];
     __shared__ float fred[32];
-    __shared__ int ired[32];
-    __shared__ int wcount[NT / 32];
-    __shared__ int base_s;
-    cg::grid_group grid = cg::this_grid();
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    __shared__ int wcnt[32];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
     const int64_t L = p.L, q = p.q;
     const int64_t pos = (q + 1 < L - 1) ? q + 1 : L - 1;
     const bool q_in_list = (q == L - 1);
-    double *acc = p.acc + 4 * p.parity, *acc_next = p.acc + 4 * (1 - p.parity);
     const bool audio = (p.sn != nullptr);
-    if (blockIdx.x == 0 && threadIdx.x < 4) {                           // the other parity's accumulators: idle now
-        acc_next[threadIdx.x] = 0.0;
-        if (threadIdx.x == 0) p.mx[1 - p.parity] = 0u;
+    const float So = (float)__ldcg(acc + 0), Sa = (float)__ldcg(acc + 1);
+    // mixed values (validate.py:524-527) and their maximum
+    float mx = -INFINITY;
+    for (int64_t w = threadIdx.x; w < L; w += blockDim.x) {
+        if (w == q && !q_in_list) continue;
+        const float on = __fdiv_rn(__ldcg(p.o + w), So);
+        const float val = audio ? __fadd_rn(__fmul_rn(p.alpha, on), __fmul_rn(p.oma, __fdiv_rn(__ldcg(p.a + w), Sa))) : on;
+        p.v[w] = val;
+        mx = fmaxf(mx, val);
     }
-    // ---- phase 1: logits (same operation order as cosine_scores_kernel) + their plain sums over the target list
+    mx = block_reduce(mx, -INFINITY, OpMax(), fred);                  // (also orders the p.v writes for this CTA)
+    const float cut = __fsub_rn(mx, __fmul_rn(p.th, mx));             // validate.py:554
+    // survivor sum + survivors per warp slice
+    const int64_t seg = (L + nw - 1) / nw;
+    const int64_t lo = int64_t(wid) * seg, hi = (lo + seg < L) ? lo + seg : L;
+    double sk = 0.0;
+    int cnt = 0;
+    for (int64_t w = lo + lane; w < hi; w += 32) {
+        if (w == q && !q_in_list) continue;
+        const float val = p.v[w];
+        if (!(val < cut)) {
+            sk += (double)val;
+            cnt += (val != 0.f) && (w != pos);
+        }
+    }
+    cnt = warp_sum(cnt);
+    if (lane == 0) wcnt[wid] = cnt;
+    sk = block_reduce(sk, 0.0, OpAdd<double>(), dred);                // (barrier: wcnt visible)
+    const float Sk = (float)sk;
+    const float vpos = p.v[pos];
+    const int pos_in = (!(vpos < cut) && vpos != 0.f) ? 1 : 0;
+    int base = pos_in, total = pos_in;
+    for (int i = 0; i < nw; ++i) {
+        const int c = wcnt[i];
+        if (i < wid) base += c;
+        total += c;
+    }
+    if (threadIdx.x == 0) {
+        if (pos_in) { p.choices[0] = (int)pos; if (p.host_cap > 0) p.host[2] = (int)pos; }
+        *p.n_choices = total;
+    }
+    // renormalise (validate.py:558) and compact in target-list order: [pos] ++ ascending(rest)
+    for (int64_t w0 = lo; w0 < hi; w0 += 32) {
+        const int64_t w = w0 + lane;
+        const bool in_list = (w < hi) && !(w == q && !q_in_list);
+        bool keep = false;
+        if (in_list) {
+            const float val = p.v[w];
+            keep = !(val < cut) && val != 0.f;
+            if (p.vals != nullptr) p.vals[w] = keep ? __fdiv_rn(val, Sk) : 0.f;
+        }
+        const bool take = keep && (w != pos);
+        const unsigned bal = __ballot_sync(0xffffffffu, take);
+        if (take) {
+            const int slot = base + __popc(bal & ((1u << lane) - 1u));
+            p.choices[slot] = (int)w;
+            if (slot < p.host_cap) p.host[2 + slot] = (int)w;
+        }
+        base += __popc(bal);
+    }
+    // publish: the list, then the count, then the sequence word the host polls
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        p.host[1] = total;
+        __threadfence_system();
+        p.host[0] = p.seq;
+    }
+}
+
+__global__ void __launch_bounds__(SELT)
+synthesis_step_kernel(const SynthStepArgs p) {
+    __shared__ double dred[32];
+    __shared__ int last_s;
+    const int lane = threadIdx.x & 31;
+    const int64_t L = p.L, q = p.q;
+    const bool q_in_list = (q == L - 1);
+    double *acc = p.acc + 4 * p.parity, *acc_next = p.acc + 4 * (1 - p.parity);
+    unsigned int *ctr = p.mx + 2 * p.parity, *ctr_next = p.mx + 2 * (1 - p.parity);   // [0] row counter, [1] CTA ticket
+    const bool audio = (p.sn != nullptr);
+    if (blockIdx.x == 0 && threadIdx.x < 4) {                          // the other parity's scratch is idle: re-arm it
+        acc_next[threadIdx.x] = 0.0;
+        if (threadIdx.x < 2) ctr_next[threadIdx.x] = 0u;
+    }
+    // ---- logits (same operation order as cosine_scores_kernel) + their plain sums over the target list.
+    // Rows are handed out dynamically, one per warp at a time: 20000 rows over 4736 resident warps would leave a
+    // 4-or-5 split (16 % idle) with a static assignment.
     double so = 0.0, sa = 0.0;
-    const int64_t warps_total = int64_t(gridDim.x) * (NT / 32);
-    for (int64_t w = int64_t(blockIdx.x) * (NT / 32) + wid; w < L; w += warps_total) {
+    unsigned int next32 = 0;
+    if (lane == 0) next32 = atomicAdd(ctr, 1u);
+    for (;;) {
+        const int64_t w = __shfl_sync(0xffffffffu, next32, 0);
+        if (w >= L) break;
+        if (lane == 0) next32 = atomicAdd(ctr, 1u);                    // the next row's ticket travels under this row's loads
         const float dot = warp_row_dot(p.tn + w * p.ld, p.qn, p.dim, lane);
         float ov = 0.f, av = 0.f;
         if (lane == 0) { ov = __fdiv_rn(dot, p.temp); p.o[w] = ov; }
@@ -258,97 +335,16 @@ synthesis_step_kernel(const SynthStepArgs p) {
     }
     so = block_reduce(so, 0.0, OpAdd<double>(), dred);
     sa = block_reduce(sa, 0.0, OpAdd<double>(), dred);
-    if (threadIdx.x == 0) { atomicAdd(acc + 0, so); atomicAdd(acc + 1, sa); }
-    grid.sync();
-    // ---- phase 2: mixed values (validate.py:524-527) and their maximum
-    const float So = (float)__ldcg(acc + 0), Sa = (float)__ldcg(acc + 1);
-    const int64_t gthreads = int64_t(gridDim.x) * NT, gtid = int64_t(blockIdx.x) * NT + threadIdx.x;
-    float mx = -INFINITY;
-    for (int64_t w = gtid; w < L; w += gthreads) {
-        if (w == q && !q_in_list) continue;
-        const float on = __fdiv_rn(__ldcg(p.o + w), So);
-        const float val = audio ? __fadd_rn(__fmul_rn(p.alpha, on), __fmul_rn(p.oma, __fdiv_rn(__ldcg(p.a + w), Sa))) : on;
-        p.v[w] = val;
-        mx = fmaxf(mx, val);
+    if (threadIdx.x == 0) {
+        atomicAdd(acc + 0, so);
+        atomicAdd(acc + 1, sa);
+        __threadfence();                                               // my rows' logits + sums before my ticket
+        last_s = (atomicAdd(ctr + 1, 1u) == gridDim.x - 1);
     }
-    mx = block_reduce(mx, -INFINITY, OpMax(), fred);
-    if (threadIdx.x == 0) atomicMax(p.mx + p.parity, order_bits(mx));
-    grid.sync();
-    // ---- phase 3: threshold (validate.py:554), survivor sum, survivors per CTA segment (contiguous windows)
-    const float mxa = unorder_bits(__ldcg(p.mx + p.parity));
-    const float cut = __fsub_rn(mxa, __fmul_rn(p.th, mxa));
-    const int64_t seg = (L + gridDim.x - 1) / gridDim.x;
-    const int64_t lo = int64_t(blockIdx.x) * seg, hi = (lo + seg < L) ? lo + seg : L;
-    double sk = 0.0;
-    int cnt = 0;
-    for (int64_t w = lo + threadIdx.x; w < hi; w += NT) {
-        if (w == q && !q_in_list) continue;
-        const float val = __ldcg(p.v + w);
-        if (!(val < cut)) {
-            sk += (double)val;
-            cnt += (val != 0.f) && (w != pos);
-        }
-    }
-    sk = block_reduce(sk, 0.0, OpAdd<double>(), dred);
-    cnt = block_reduce(cnt, 0, OpAdd<int>(), ired);
-    if (threadIdx.x == 0) { if (sk != 0.0) atomicAdd(acc + 2, sk); p.counts[blockIdx.x] = cnt; }
-    grid.sync();
-    // ---- phase 4: renormalise (validate.py:558) and compact in target-list order: [pos] ++ ascending(rest)
-    const float Sk = (float)__ldcg(acc + 2);
-    const float vpos = __ldcg(p.v + pos);
-    const int pos_in = (!(vpos < cut) && vpos != 0.f) ? 1 : 0;
-    int before = 0, total = 0;
-    for (int c = threadIdx.x; c < (int)gridDim.x; c += NT) {
-        const int k = __ldcg(p.counts + c);
-        total += k;
-        if (c < (int)blockIdx.x) before += k;
-    }
-    before = block_reduce(before, 0, OpAdd<int>(), ired);
-    total = block_reduce(total, 0, OpAdd<int>(), ired);
-    if (threadIdx.x == 0) base_s = pos_in + before;
     __syncthreads();
-    const int n_total = pos_in + total;
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
-        if (pos_in) { p.choices[0] = (int)pos; if (p.host_cap > 0) p.host[2] = (int)pos; }
-        *p.n_choices = n_total;
-    }
-    for (int64_t w0 = lo; w0 < hi; w0 += NT) {
-        const int64_t w = w0 + threadIdx.x;
-        const bool in_list = (w < hi) && !(w == q && !q_in_list);
-        float val = 0.f;
-        bool keep = false;
-        if (in_list) {
-            val = __ldcg(p.v + w);
-            keep = !(val < cut) && val != 0.f;
-            if (p.vals != nullptr) p.vals[w] = keep ? __fdiv_rn(val, Sk) : 0.f;
-        }
-        const bool take = keep && (w != pos);
-        const unsigned bal = __ballot_sync(0xffffffffu, take);
-        if (lane == 0) wcount[wid] = __popc(bal);
-        __syncthreads();
-        int off = base_s;
-        for (int i = 0; i < wid; ++i) off += wcount[i];
-        if (take) {
-            const int slot = off + __popc(bal & ((1u << lane) - 1u));
-            p.choices[slot] = (int)w;
-            if (slot < p.host_cap) p.host[2 + slot] = (int)w;
-        }
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            int t = 0;
-            for (int i = 0; i < NT / 32; ++i) t += wcount[i];
-            base_s += t;
-        }
-        __syncthreads();
-    }
-    // ---- publish: every CTA's host writes must be visible before the sequence word
-    __threadfence_system();
-    grid.sync();
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
-        p.host[1] = n_total;
-        __threadfence_system();
-        p.host[0] = p.seq;
-    }
+    if (!last_s) return;
+    __threadfence();                                                   // acquire side of the ticket
+    synthesis_select(p, acc);
 }
 
 // sims[w] = <x_w, d> / (||x_w|| * ||d||)   (fp64 accumulation), one warp per row.
@@ -436,26 +432,20 @@ extern "C" int avtex_synthesis_step(const float *tn, int64_t ld, int64_t L, int6
     AVTEX_REQUIRE(ws_f32 != nullptr && ws_acc != nullptr && ws_max != nullptr && ws_counts != nullptr &&
                       choices != nullptr && n_choices != nullptr && host_out != nullptr && host_cap >= 0,
                   "synthesis_step: workspace / output pointers must not be NULL");
-    int sms = 0, cc = 0, per_sm = 0, coop = 0;
+    int sms = 0, cc = 0;
     if (int rc = avtex_device_info(device, &sms, &cc)) return rc;
-    AVTEX_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device));
-    AVTEX_REQUIRE(coop != 0, "synthesis_step: device does not support cooperative launch");
-    AVTEX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, synthesis_step_kernel, NT, 0));
-    AVTEX_REQUIRE(per_sm >= 1, "synthesis_step: kernel does not fit on an SM");
-    if (per_sm > 4) per_sm = 4;                      // 32 warps per SM stream the table; more only lengthens the barriers
-    int64_t grid = (int64_t)sms * per_sm;
-    const int64_t need = (L + NT / 32 - 1) / (NT / 32);
+    int64_t grid = (int64_t)sms;                     // one 1024-thread CTA per SM: 32 warps each stream the table
+    const int64_t need = (L + SELT / 32 - 1) / (SELT / 32);
     if (grid > need) grid = need;
-    AVTEX_REQUIRE(ws_counts_len >= grid, "synthesis_step: ws_counts needs %lld entries", (long long)grid);
+    (void)ws_counts_len;
     SynthStepArgs p;
     p.tn = tn; p.ld = ld; p.L = L; p.dim = dim; p.qn = qn; p.sn = sn; p.lds = lds; p.dimA = dimA; p.dn = dn;
     p.temp = temp; p.alpha = alpha; p.oma = one_minus_alpha; p.th = th; p.q = q;
     p.o = ws_f32; p.a = ws_f32 + L; p.v = ws_f32 + 2 * L;
     p.acc = ws_acc; p.mx = ws_max; p.counts = ws_counts; p.choices = choices; p.n_choices = n_choices; p.vals = vals;
     p.host = host_out; p.host_cap = host_cap; p.seq = seq; p.parity = seq & 1;
-    void *args[] = {(void *)&p};
-    AVTEX_CUDA(cudaLaunchCooperativeKernel((void *)synthesis_step_kernel, dim3((unsigned)grid), dim3(NT), args, 0,
-                                           as_stream(stream)));
+    synthesis_step_kernel<<<(unsigned)grid, SELT, 0, as_stream(stream)>>>(p);
+    AVTEX_LAUNCH_CHECK();
     return 0;
 }
 

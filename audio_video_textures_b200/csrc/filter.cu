@@ -140,7 +140,8 @@ struct S1Cfg {
     static constexpr int VEC_PER_ROW = PITCH / 4;
     static constexpr int CHUNK_VECS = CH * VEC_PER_ROW;
     static constexpr int STAGES = 6;
-    static constexpr int SMEM_BYTES = STAGES * CH * PITCH * 4;
+    static constexpr int IN_BYTES = STAGES * CH * PITCH * 4;
+    static constexpr int SMEM_BYTES = IN_BYTES + CH * FT * 4;        // + per-thread output staging [CH][FT]
     static_assert(FS % 2 == 0 && PER % NCH == 0, "sliding-window filter needs FS even and (FS + 2) % 3 == 0");
 };
 
@@ -158,6 +159,10 @@ diag_filter_s1_kernel(const float *__restrict__ D1, int64_t ld1, int64_t in_row0
                       int64_t a0, int64_t rows_out, int64_t m, float *__restrict__ D2, int64_t ld2,
                       float *__restrict__ D3, int64_t ld3, float p, double *sum, unsigned long long *nnz, int nb) {
     using C = S1Cfg<FS>;
+#ifndef AVTEX_S1_UR_PAIRS
+#define AVTEX_S1_UR_PAIRS 0
+#endif
+    constexpr int UR_PAIRS = AVTEX_S1_UR_PAIRS < FS + 1 ? AVTEX_S1_UR_PAIRS : FS + 1;
     constexpr int KV = (C::CHUNK_VECS + FT - 1) / FT;                 // 128-bit copies per thread per chunk
     extern __shared__ __align__(16) float s1_smem[];
     __shared__ double sred[32];
@@ -226,16 +231,23 @@ diag_filter_s1_kernel(const float *__restrict__ D1, int64_t ld1, int64_t in_row0
     float2 wp[FS + 1];
 #pragma unroll
     for (int q = 0; q <= FS; ++q) {
-        wp[q].x = *reinterpret_cast<volatile float *>(&wp_s[q].x);
-        wp[q].y = *reinterpret_cast<volatile float *>(&wp_s[q].y);
+        if (q < UR_PAIRS) {            // constant-bank values: ptxas keeps these pairs in UNIFORM registers (no vector registers)
+            wp[q] = make_float2(q < FS ? taps.w[q] : 0.f, q >= 1 ? taps.w[q - 1] : 0.f);
+        } else {
+            wp[q].x = *reinterpret_cast<volatile float *>(&wp_s[q].x);
+            wp[q].y = *reinterpret_cast<volatile float *>(&wp_s[q].y);
+        }
     }
     float2 acc[C::NP];
 #pragma unroll
     for (int sidx = 0; sidx < C::NP; ++sidx) acc[sidx] = make_float2(0.f, 0.f);
 
-    // ---- outputs: local index i <-> (a_band + i, c_thread + i); valid i in [i_lo, i_hi).  The pair emitted at
-    // input step t holds outputs i = t - FS and t - FS + 1; emissions come in increasing i, so the destination
-    // pointers simply advance by 2 * (ld + 1) per emission.
+    // ---- outputs: local index i <-> (a_band + i, c_thread + i); valid i in [i_lo, i_lo + i_span).  The pair
+    // completed at input step t holds outputs i = t - FS and t - FS + 1.  Completed values are parked in a
+    // per-thread column of shared memory (compile-time offsets) and written out by a small ROLLED loop after each
+    // chunk: predicate, D2 store, pow, D3 store and the sigma statistics exist once in the code and their
+    // addresses advance by ld + 1 per output (the fully unrolled form re-derived every address with 64-bit
+    // multiplies and re-read the parameters: ~45 instructions per pair, measured).
     const int64_t lim_i = ((a0 + rows_out < a_band + band) ? a0 + rows_out : a_band + band) - a_band;
     const int64_t lo64 = c_thread < 0 ? -c_thread : 0, hi64 = (m - c_thread < lim_i) ? m - c_thread : lim_i;
     const int i_lo = int(lo64);
@@ -243,6 +255,7 @@ diag_filter_s1_kernel(const float *__restrict__ D1, int64_t ld1, int64_t in_row0
     const int64_t step2 = ld2 + 1, step3 = ld3 + 1;
     float *o2 = D2 + (a_band - a0) * ld2 + c_thread - int64_t(FS) * step2;     // i = -FS (never dereferenced while invalid)
     float *o3 = POW ? D3 + (a_band - a0) * ld3 + c_thread - int64_t(FS) * step3 : nullptr;
+    float *out_s = s1_smem + C::IN_BYTES / 4 + threadIdx.x;                     // out_s[r * FT]: my value of chunk row r
     int i0 = -FS;
     double s = 0.0;
     int z = 0;
@@ -267,27 +280,25 @@ diag_filter_s1_kernel(const float *__restrict__ D1, int64_t ld1, int64_t in_row0
                 for (int sidx = 0; sidx < C::NP; ++sidx) {
                     const int q = (tb - 2 * sidx + 2 * C::PER) % C::PER;          // tap-pair index for slot sidx at this step
                     if (q <= FS) acc[sidx] = __ffma2_rn(wp[q], x2, acc[sidx]);
-                    if (q == FS) {                                     // slot complete
-                        const float2 v = acc[sidx];
+                    if (q == FS) {                                     // slot complete: rows r and r + 1 of this chunk's outputs
+                        static_assert(C::CH % 2 == 0, "pairs must not straddle chunks");
+                        out_s[r * FT] = acc[sidx].x;
+                        out_s[(r + 1) * FT] = acc[sidx].y;
                         acc[sidx] = make_float2(0.f, 0.f);
-                        const bool ok0 = unsigned(i0 - i_lo) < i_span, ok1 = unsigned(i0 + 1 - i_lo) < i_span;
-                        if (ok0) o2[0] = v.x;
-                        if (ok1) o2[step2] = v.y;
-                        if (POW) {
-                            const float y0 = pow_pos_call(v.x, p), y1 = pow_pos_call(v.y, p);   // unconditional: no divergence
-                            if (ok0) o3[0] = y0;
-                            if (ok1) o3[step3] = y1;
-                            o3 += 2 * step3;
-                        }
-                        if (STATS) {
-                            const float v0 = ok0 ? v.x : 0.f, v1 = ok1 ? v.y : 0.f;
-                            fs += v0 + v1;                             // fp32 inside one body, fp64 across bodies
-                            z += (v0 != 0.f) + (v1 != 0.f);
-                        }
-                        o2 += 2 * step2;
-                        i0 += 2;
                     }
                 }
+            }
+#pragma unroll 2
+            for (int r = 0; r < C::CH; ++r) {
+                const float v = out_s[r * FT];
+                if (unsigned(i0 - i_lo) < i_span) {
+                    *o2 = v;
+                    if (POW) *o3 = pow_pos(v, p);
+                    if (STATS) { fs += v; z += (v != 0.f); }
+                }
+                o2 += step2;
+                if (POW) o3 += step3;
+                ++i0;
             }
         }
         s += (double)fs;

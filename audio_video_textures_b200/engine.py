@@ -8,6 +8,7 @@ PyTorch arithmetic: a missing library or a failed kernel raises.
 from __future__ import annotations
 
 import ctypes as C
+import functools
 from dataclasses import dataclass
 
 import numpy as np
@@ -322,9 +323,17 @@ def csr_from_matrix(P: torch.Tensor, counts: torch.Tensor | None = None):
 
 
 # --------------------------------------------------------------------------- K2
+@functools.lru_cache(maxsize=64)
+def _binomial_taps_cached(filter_size: int) -> np.ndarray:
+    taps = np.asarray((np.poly1d([0.5, 0.5]) ** (filter_size - 1)).coeffs, dtype=np.float32).reshape(-1)
+    taps.setflags(write=False)
+    return taps
+
+
 def binomial_taps(filter_size: int) -> np.ndarray:
-    """classic/computeD2.py:34 — coeffs((0.5 x + 0.5)^(fs-1)) evaluated in float64, cast to fp32."""
-    return np.asarray((np.poly1d([0.5, 0.5]) ** (filter_size - 1)).coeffs, dtype=np.float32).reshape(-1)
+    """classic/computeD2.py:34 — coeffs((0.5 x + 0.5)^(fs-1)) evaluated in float64, cast to fp32.  Cached: the
+    polynomial power costs ~0.6 ms of host time at fs = 40, which sat in front of every filter launch."""
+    return _binomial_taps_cached(int(filter_size))
 
 
 def filtered_size(n: int, filter_size: int, stride: int) -> int:
@@ -512,7 +521,7 @@ class SynthesisWorkspace:
         self.L, self.host_cap = L, min(L, host_cap)
         self.f32 = torch.empty(3 * L, dtype=torch.float32, device=device)
         self.acc = torch.zeros(8, dtype=torch.float64, device=device)
-        self.mx = torch.zeros(2, dtype=torch.int32, device=device)
+        self.mx = torch.zeros(4, dtype=torch.int32, device=device)
         self.counts = torch.zeros(4096, dtype=torch.int32, device=device)
         self.sel = torch.zeros(L + 1, dtype=torch.int32, device=device)         # [count | choices...]
         self.host = torch.zeros(2 + self.host_cap, dtype=torch.int32).pin_memory()

@@ -244,13 +244,13 @@ AVTEX_API int avtex_cosine_scores(const float *tn, int64_t ld, int64_t rows, int
 AVTEX_API int avtex_select_step(const float *o, const float *a, int64_t L, int64_t q, float alpha,
                       float one_minus_alpha, float th, int *choices, int *n_choices, float *vals,
                       int device, void *stream);
-/* ONE launch per synthesis step (cooperative kernel): avtex_cosine_scores on the window table (and on the
+/* ONE launch per synthesis step: avtex_cosine_scores on the window table (and on the
  * source-audio table against the driving row when sn/dn != NULL) fused with avtex_select_step — same arithmetic,
  * same survivor list.  The list goes to choices / n_choices on the device AND, without a copy or a stream
  * synchronisation, to MAPPED PINNED host memory: host_out = [seq, n, first host_cap survivors]; the sequence
  * word `seq` is written last (after __threadfence_system), the host polls it.  Workspaces (device): ws_f32
- * 3*L floats; ws_acc 8 doubles and ws_max 2 uint32, ZEROED once before the first step (the kernel re-arms the
- * other parity itself; seq must increase by 1 per call); ws_counts >= 4 * #SM ints.
+ * 3*L floats; ws_acc 8 doubles and ws_max 4 uint32 (row counter + CTA ticket per parity), ZEROED once before the
+ * first step (the kernel re-arms the other parity itself; seq must increase by 1 per call); ws_counts unused.
  * replaces: cvt/models/models.py:351-352,412-417,433-457 + cvt/validate.py:369-378,524-527,554,558,568 per step. */
 AVTEX_API int avtex_synthesis_step(const float *tn, int64_t ld, int64_t L, int64_t dim, const float *qn,
                          const float *sn, int64_t lds, int64_t dimA, const float *dn, float temp,

@@ -1,0 +1,92 @@
+"""Kernel-level driver for ncu captures and A/B timing (round 2).
+    python profiles/r02_kernels.py filter1 [N]     stride-1 filter + pow at N frames (default 16000 -> M = 15961)
+    python profiles/r02_kernels.py filter4         stride-4 filter on the C5 row-shard shape (12576 x 100000 D1 rows)
+    python profiles/r02_kernels.py norms           K0 on the C5 clip (100000 rows of 12288 B)
+    python profiles/r02_kernels.py gram5 [rows]    K1 on a C5 row shard (rows x 100000, K = 12288)
+    python profiles/r02_kernels.py synth           150 fused synthesis steps at C3 with per-step kernel time
+Environment switches read by the library: AVTEX_FILTER_S1=0 (old stride-1 kernel), AVTEX_NORMS_G=32|64|128|256.
+Prints CUDA-event medians; run under ncu for per-launch counters."""
+import os
+import sys
+import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+
+from audio_video_textures_b200 import engine
+from audio_video_textures_b200.synth import synth_embeddings, synth_video_cuda
+
+what = sys.argv[1]
+HBM = 6547.8
+
+
+def timed(fn, reps=5):
+    ms = []
+    for _ in range(reps + 2):
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        ev[0].record()
+        r = fn()
+        ev[1].record()
+        torch.cuda.synchronize()
+        ms.append(ev[0].elapsed_time(ev[1]))
+    return float(np.median(ms[2:])), r
+
+
+if what == "filter1":
+    n = int(sys.argv[2]) if len(sys.argv) > 2 else 16000
+    D1 = engine.empty_matrix(n, n, "cuda")
+    D1.uniform_(100.0, 20000.0)
+    m = n - 39
+    for stats in (False, True):
+        st = engine.new_stats("cuda") if stats else None
+        ms, _ = timed(lambda: engine.diag_filter(D1, 40, 1, p=0.7, stats=st))
+        b = 4.0 * n * n + 8.0 * m * m
+        print(f"filter1 N={n} stats={stats} s1={os.environ.get('AVTEX_FILTER_S1', '1')}: {ms:.3f} ms  {b / ms / 1e6:.0f} GB/s  {b / ms / 1e6 / HBM:.3f} of HBM")
+elif what == "filter4":
+    rows, n = 12576, 100000
+    D1 = torch.empty((rows, n), dtype=torch.float32, device="cuda").uniform_(100.0, 20000.0)
+    m = (n - 40) // 4 + 1
+    ro = (rows - 40) // 4 + 1
+    ms, _ = timed(lambda: engine.diag_filter(D1, 40, 4, p=0.7, m=m, a0=0, rows_out=ro, in_row0=0))
+    b = 4.0 * rows * n + 8.0 * ro * m
+    print(f"filter4 shard: {ms:.3f} ms  {b / ms / 1e6:.0f} GB/s  {b / ms / 1e6 / HBM:.3f} of HBM")
+elif what == "norms":
+    frames = synth_video_cuda(100000, 64, 64, seed=0)
+    x = frames.reshape(100000, -1)
+    sq = torch.empty(100000, dtype=torch.int64, device="cuda")
+    fl = torch.zeros(2, dtype=torch.int64, device="cuda")
+    ms, _ = timed(lambda: engine.frame_norms_rows(x, 0, 100000, sq, fl))
+    b = float(x.numel())
+    print(f"norms G={os.environ.get('AVTEX_NORMS_G', 'default')}: {ms:.3f} ms  {b / ms / 1e6:.0f} GB/s  {b / ms / 1e6 / HBM:.3f} of HBM")
+elif what == "gram5":
+    rows = int(sys.argv[2]) if len(sys.argv) > 2 else 12536
+    frames = synth_video_cuda(100000, 64, 64, seed=0)
+    pf = engine.pack_frames(frames)
+    D = engine.empty_matrix(rows, 100000, "cuda")
+    ms, _ = timed(lambda: engine.gram_l2(pf, 0, rows, symmetric=False, out=D), reps=3)
+    ops = 2.0 * rows * 100000 * 12288
+    print(f"gram5 {rows} x 100000 K=12288: {ms:.3f} ms  {ops / ms / 1e9:.0f} TOP/s")
+elif what == "synth":
+    from audio_video_textures_b200.contrastive.validate import SynthesisState
+    L, D = 20000, 2304
+    emb = synth_embeddings(L, D, seed=0, device="cuda")
+    st = SynthesisState(emb)
+    np.random.seed(0)
+    q = 10
+    kern, wall = [], []
+    for it in range(1, 160):
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        t0 = time.perf_counter()
+        ev[0].record()
+        ch = st.step(q, it, 0.1, 0.5, 0.3)
+        ev[1].record()
+        t1 = time.perf_counter()
+        q = int(np.random.choice(ch))
+        t2 = time.perf_counter()
+        torch.cuda.synchronize()
+        kern.append(ev[0].elapsed_time(ev[1]) * 1e3)
+        wall.append(((t1 - t0) * 1e6, (t2 - t1) * 1e6))
+    w = np.array(wall[10:])
+    print(f"synth C3: kernel (events) median {np.median(kern[10:]):.1f} us; host step() {np.median(w[:, 0]):.1f} us; "
+          f"np.random.choice {np.median(w[:, 1]):.1f} us")

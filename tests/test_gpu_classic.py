@@ -183,7 +183,7 @@ def test_diag_filter_matches_reference(eng, name):
     np.testing.assert_allclose(D3.cpu().numpy(), (D2.cpu() ** 0.7).numpy(), rtol=1e-5)
     total, nnz = eng.read_stats(stats)
     assert nnz == int((D2 != 0).sum())
-    np.testing.assert_allclose(total, D2.double().sum().item(), rtol=1e-12)
+    np.testing.assert_allclose(total, D2.double().sum().item(), rtol=1e-8)    # fp32 partials inside a band, fp64 across
     np.testing.assert_array_equal(eng.binomial_taps(fs), g["ref_filter_diag"])
     # row-sharded call with a halo'd D1 block gives the same rows
     m = D2.shape[0]

@@ -36,7 +36,7 @@ def _check(n, h, w, fs, stride, world, calls=1):
 
 
 @pytest.mark.parametrize("world", [2, 4, 8])
-@pytest.mark.parametrize("n,h,w,fs,stride", [(700, 16, 16, 40, 4), (2051, 8, 8, 40, 4), (1500, 12, 20, 16, 1)])
+@pytest.mark.parametrize("n,h,w,fs,stride", [(900, 16, 16, 40, 4), (2051, 8, 8, 40, 4), (1500, 12, 20, 16, 1)])
 def test_virtual_ranks_equal_single_gpu(n, h, w, fs, stride, world):
     _check(n, h, w, fs, stride, world)
 
