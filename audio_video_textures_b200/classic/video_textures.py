@@ -31,18 +31,23 @@ def texture_walk(P, model_type: int, fps: int, new_video_length: int, stride: in
 
     The reference calls `P[this].nonzero().cpu()` (a device sync) on every step; here the ordered
     survivor lists of ALL rows are compacted once on the GPU (avtex_row_nnz / avtex_csr_fill) and
-    the walk runs on the host.  The draw itself stays `np.random.choice` on numpy's global legacy
+    the walk runs on the host — or, for matrices whose survivor lists run to gigabytes, `P` is an
+    engine.SurvivorRows that fetches only the visited rows.  The draw itself stays `np.random.choice` on numpy's global legacy
     generator, so the sequence is bit-identical to the reference under the same `np.random.seed`.
     Returns (new_frames_list, jump_count).
     """
-    if isinstance(P, tuple):
-        rowptr, colidx = P
+    if isinstance(P, engine.SurvivorRows):                 # lazy: only the rows the walk visits are compacted / copied
+        n_rows = len(P)
+        survivors = P.__getitem__
     else:
-        rowptr, colidx = engine.csr_from_matrix(P if P.is_cuda else P.cuda())
-    n_rows = len(rowptr) - 1
+        if isinstance(P, tuple):
+            rowptr, colidx = P
+        else:
+            rowptr, colidx = engine.csr_from_matrix(P if P.is_cuda else P.cuda())
+        n_rows = len(rowptr) - 1
 
-    def survivors(i):
-        return colidx[rowptr[i]:rowptr[i + 1]]
+        def survivors(i):
+            return colidx[rowptr[i]:rowptr[i + 1]]
 
     new_video_length = fps * new_video_length
     jump_count = 0

@@ -274,6 +274,18 @@ class SymmetricShardWorkspace(PeerBuffers):
         buf = self.hdl.get_buffer(r, (self.rows_max, self.ld), torch.float32)
         return buf[row_off:row_off + rows]
 
+    def p3n(self) -> torch.Tensor:
+        """This rank's P3_new shard [shard, mpad] in symmetric memory (allocated on first use, collectively)."""
+        if getattr(self, "_p3n", None) is None:
+            import torch.distributed._symmetric_memory as symm_mem
+            self._p3n = symm_mem.empty((self.plan.shard, self.mpad), dtype=torch.float32, device=self.device)
+            self._hdl_p3n = symm_mem.rendezvous(self._p3n, self.group.group_name)
+        return self._p3n
+
+    def peer_p3n(self, r: int) -> torch.Tensor:
+        self.p3n()
+        return self._hdl_p3n.get_buffer(r, (self.plan.shard, self.mpad), torch.float32)
+
 
 class RankStep:
     """One rank's classic++ step, phase by phase.  Phases of different ranks are separated by barriers (real
@@ -413,11 +425,12 @@ class ShardResult:
         return self.fc.eps_trail
 
 
-def _probabilities(res: ShardResult, stats: torch.Tensor, sigma_factor, threshold):
+def _probabilities(res: ShardResult, stats: torch.Tensor, sigma_factor, threshold, Pn_out=None):
     own = res.plan.a1 - res.plan.a0
     res.sigma = engine.sigma_from_stats(*engine.read_stats(stats), sigma_factor)
     res.P3, res.P3_new, res.counts = engine.transition_probs(
-        res.D3_new, res.sigma, shift=1, rows_out=own, threshold=threshold, want_counts=threshold is not None)
+        res.D3_new, res.sigma, shift=1, rows_out=own, threshold=threshold, want_counts=threshold is not None,
+        Pn_out=Pn_out)
     res.launches += 1
 
 
@@ -509,8 +522,24 @@ def classic_sharded(frames: torch.Tensor, filter_size: int, stride: int, rank: i
     if sigma_factor is not None:
         if world > 1:
             stats = allreduce_stats(stats, group)
-        _probabilities(res, stats, sigma_factor, threshold)
+        # with a workspace P3_new goes into peer-mapped memory, so the host that runs the walk can read any rank's rows
+        Pn_out = workspace.p3n() if (workspace is not None and world > 1 and threshold is not None) else None
+        _probabilities(res, stats, sigma_factor, threshold, Pn_out)
     return res
+
+
+def sharded_survivor_rows(res: ShardResult, workspace: "SymmetricShardWorkspace") -> engine.SurvivorRows:
+    """Survivor lists over ALL ranks' P3_new shards, fetched on demand through peer-mapped memory (one-sided: the
+    owning rank does nothing).  Call on the rank whose host runs the walk, after `workspace.barrier(2)` on every
+    rank (all shards complete)."""
+    plan = res.plan
+    views = [workspace.peer_p3n(r) for r in range(plan.world)]
+
+    def row(i):
+        r = min(i // plan.shard, plan.world - 1)
+        return views[r][i - r * plan.shard, :plan.m]
+
+    return engine.SurvivorRows(plan.m, row)
 
 
 def gather_survivors(res: ShardResult, group=None):

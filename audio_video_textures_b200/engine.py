@@ -293,12 +293,16 @@ def pairwise_l2(frames: torch.Tensor, row0: int = 0, rows: int | None = None,
 
 # --------------------------------------------------------------------------- K5
 def transition_probs(D: torch.Tensor, sigma, shift: int = 1, rows_out: int | None = None,
-                     threshold: float | None = None, want_P: bool = True, want_counts: bool = False):
-    """P (and thresholded P_new) for output rows [0, rows_out) from source rows min(i+shift, rows-1)."""
+                     threshold: float | None = None, want_P: bool = True, want_counts: bool = False,
+                     Pn_out: torch.Tensor | None = None):
+    """P (and thresholded P_new) for output rows [0, rows_out) from source rows min(i+shift, rows-1).
+    `Pn_out`: caller-provided [rows_out, cols] destination of P_new (e.g. a peer-mapped symmetric buffer)."""
     rows_in, cols = D.shape
     rows_out = rows_in if rows_out is None else rows_out
     P = empty_matrix(rows_out, cols, D.device) if want_P else None
-    Pn = empty_matrix(rows_out, cols, D.device) if threshold is not None else None
+    Pn = None
+    if threshold is not None:
+        Pn = empty_matrix(rows_out, cols, D.device) if Pn_out is None else Pn_out[:rows_out, :cols]
     counts = torch.empty(rows_out, dtype=torch.int32, device=D.device) if want_counts else None
     th = _f32(threshold) if threshold is not None else np.float32(-1.0)
     _lib.call("avtex_transition_probs", _lib.ptr(D), D.stride(0), rows_in, cols, C.c_float(_f32(sigma)), shift,
@@ -320,6 +324,35 @@ def csr_from_matrix(P: torch.Tensor, counts: torch.Tensor | None = None):
     _lib.call("avtex_csr_fill", _lib.ptr(P), P.stride(0), rows, cols, _lib.ptr(rowptr), _lib.ptr(colidx),
               _dev(P), _stream(P))
     return rowptr.cpu().numpy(), colidx[:total].cpu().numpy()
+
+
+class SurvivorRows:
+    """The survivor lists (ascending non-zero columns per row of P3_new) the sampling walk draws from, fetched ON
+    DEMAND: `rows[i]` compacts row i on the device and copies only that list to the host (cached).  The reference
+    does the same per step (`P[this_frame].nonzero().cpu()`, classic/video_textures.py:76-78); at N = 100000 about
+    half of the 6.2e8 entries survive the default threshold, so copying every list (1.2 GB) for a 900-frame walk
+    would dominate the whole pipeline.  `row_fn(i)` returns a CUDA fp32 view of row i (local shard or a peer-mapped
+    row of another GPU's shard)."""
+
+    def __init__(self, n_rows: int, row_fn):
+        self.n_rows, self._row_fn, self._cache, self.fetched = n_rows, row_fn, {}, 0
+
+    def __len__(self):
+        return self.n_rows
+
+    def __getitem__(self, i: int) -> np.ndarray:
+        i = int(i)
+        got = self._cache.get(i)
+        if got is None:
+            row = self._row_fn(i)
+            got = torch.nonzero(row).view(-1).to(torch.int32).cpu().numpy()
+            self._cache[i] = got
+            self.fetched += 1
+        return got
+
+    @classmethod
+    def from_matrix(cls, P: torch.Tensor) -> "SurvivorRows":
+        return cls(P.shape[0], lambda i: P[i])
 
 
 # --------------------------------------------------------------------------- K2

@@ -13,7 +13,8 @@ Main line
   One "step" = norms (K0) -> tcgen05 Gram + L2 epilogue (K1) -> diagonal filter + pow (K2) -> all future-cost
   sweeps in one cooperative kernel (K3) -> finalize (K4).  `value` is timed with the byte frames resident in
   HBM; `e2e` goes through the reference-named entry points from PINNED HOST frames and includes sigma3 / P3 /
-  P3_new and the survivor lists copied back to the host — the SAME scope at every N.
+  P3_new, the survivor lists the walk needs copied back to the host and the 900-frame walk itself — the SAME
+  scope at every N.
 Extra records on the same JSON line (all measured in this run)
   roofline      the Gram kernel: executed int8 ops against an int8 peak MEASURED here (cuBLASLt int8 GEMM and a
                 long-K run of the kernel itself), algorithmic ops separately, the SM clock measured INSIDE the
@@ -415,6 +416,26 @@ def synth_records(dev, state_c2):
     return rec
 
 
+def _walk_sharded(avdist, engine, res, workspace, wl, rank):
+    """The walk of the e2e legs at N > 1: rank 0's host draws from survivor lists fetched on demand out of the
+    owning ranks' P3_new shards (peer-mapped symmetric memory); without a workspace the lists are all-gathered.
+    Returns the bytes copied device -> host on rank 0."""
+    from audio_video_textures_b200.classic.video_textures import texture_walk
+    if workspace is None:
+        rowptr, colidx = avdist.gather_survivors(res)
+        if rank == 0:
+            np.random.seed(0)
+            texture_walk((rowptr, colidx), wl["m"], 30, 30, wl["stride"], wl["fs"])
+        return rowptr.nbytes + colidx.nbytes
+    workspace.barrier(2)                                   # every rank's P3_new shard is complete
+    if rank != 0:
+        return 0
+    rows = avdist.sharded_survivor_rows(res, workspace)
+    np.random.seed(0)
+    texture_walk(rows, wl["m"], 30, 30, wl["stride"], wl["fs"])
+    return int(sum(v.nbytes for v in rows._cache.values()))
+
+
 def c5_record(args, dev, rank, world, peaks):
     """configs[4] at THIS N: 100000 frames 64x64, -m 3 -fs 40 -stride 4 (M = 24991).  Strong scaling: the same
     clip at every N, rows sharded over the ranks (N = 1: the single-GPU path, D1 = 40 GB resident)."""
@@ -495,18 +516,21 @@ def c5_record(args, dev, rank, world, peaks):
             stats = engine.new_stats(dev)
             D3n = engine.future_cost_finalize(D3, fc.mvec, 0.997, stats=stats)
             sigma = engine.sigma_from_stats(*engine.read_stats(stats), 4.5)
-            P3, P3n, counts = engine.transition_probs(D3n, sigma, threshold=0.08, want_P=False, want_counts=True)
-            rowptr, colidx = engine.csr_from_matrix(P3n, counts)
-            del D1, D2, D3, D3n, P3n
+            P3, P3n, counts = engine.transition_probs(D3n, sigma, threshold=0.08, want_counts=True)
+            rows = engine.SurvivorRows.from_matrix(P3n)     # 3e8 survivors: only the visited rows travel
+            from audio_video_textures_b200.classic.video_textures import texture_walk
+            np.random.seed(0)
+            texture_walk(rows, wl["m"], 30, 30, stride, fs)
+            d2h = int(sum(v.nbytes for v in rows._cache.values()))
+            del D1, D2, D3, D3n, P3, P3n
         else:
             res = avdist.classic_sharded(dev_frames, fs, stride, rank, world, sigma_factor=4.5, threshold=0.08,
                                          workspace=ws)
-            rowptr, colidx = avdist.gather_survivors(res)
+            d2h = _walk_sharded(avdist, engine, res, ws, wl, rank)
             del res
         sync_all()
         if it >= 1:
             e2e_ms.append(1e3 * (time.perf_counter() - t0))
-        d2h = rowptr.nbytes + colidx.nbytes
     t_e2e = torch.tensor([float(np.mean(e2e_ms))], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
@@ -518,7 +542,8 @@ def c5_record(args, dev, rank, world, peaks):
             "stages_ms_max_over_ranks": stages,
             "e2e": {"ms_per_step": float(t_e2e.item()), "value": n * n / (float(t_e2e.item()) * 1e-3),
                     "h2d_bytes_per_step": int(host.numel()), "d2h_bytes_per_step": int(d2h),
-                    "includes": "pinned host clip -> HBM, norms, Gram, filter, future cost, sigma3, P3_new, survivor CSR on the host"},
+                    "includes": "pinned host clip -> HBM, norms, Gram, filter, future cost, sigma3, P3, P3_new, the 900-frame "
+                                "-m 3 walk over survivor lists fetched on demand"},
             "l2": "256 MB L2 flush between timed steps"}
 
 
@@ -661,6 +686,7 @@ def run_ours(args):
         from audio_video_textures_b200.classic.computeD1 import compute_D1
         from audio_video_textures_b200.classic.computeD2 import compute_D2
         from audio_video_textures_b200.classic.q_learning import LAST, q_learning
+        from audio_video_textures_b200.classic.video_textures import texture_walk
         host4 = host.view(n, wl["h"], wl["w"], 3)
         for it in range(reps):
             flush.fill_(1)
@@ -674,6 +700,8 @@ def run_ours(args):
                     D2, P2, s2, _ = compute_D2(D1, f, filter_size=fs, stride=stride)
                 D3n, P3, P3n, s3 = q_learning(D2, f, thresholding=0.08)
             rowptr, colidx = engine.csr_from_matrix(P3n, LAST["counts"])          # what the walk consumes (D2H)
+            np.random.seed(0)
+            walk, _ = texture_walk((rowptr, colidx), wl["m"], 30, 30, stride, fs)
             sig = s3.item()
             torch.cuda.synchronize()
             if it >= args.warmup:
@@ -681,7 +709,8 @@ def run_ours(args):
             d2h = rowptr.nbytes + colidx.nbytes + 3 * 4
         state.update(P3n=P3n, counts=LAST["counts"])
         t_e2e = float(np.mean(times))
-        includes = "compute_D1+compute_D2+q_learning (P1,P2,P3,P3_new, sigmas) + survivor CSR D2H"
+        includes = ("compute_D1+compute_D2+q_learning (P1,P2,P3,P3_new, sigmas) + survivor lists D2H + the "
+                    f"{len(walk)}-frame -m {wl['m']} walk")
     else:
         for it in range(reps):
             flush.fill_(1)
@@ -690,16 +719,16 @@ def run_ours(args):
             dev_frames = avdist.load_frames_sharded(host, rank, world, dev)     # 1/G over PCIe + NVLink all-gather
             res = avdist.classic_sharded(dev_frames, fs, stride, rank, world, sigma_factor=f, threshold=0.08,
                                          workspace=workspace)
-            rowptr, colidx = avdist.gather_survivors(res)
+            d2h = _walk_sharded(avdist, engine, res, workspace, wl, rank)
             sync_all()
             if it >= args.warmup:
                 times.append(time.perf_counter() - t0)
-            d2h = rowptr.nbytes + colidx.nbytes + 4
         t = torch.tensor([float(np.mean(times))], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         t_e2e = float(t.item())
         includes = ("each rank copies 1/G of the pinned host clip, NVLink all-gather replicates it; sharded norms / "
-                    "Gram / filter / future cost; sigma3 (all-reduce), P3, P3_new; survivor CSR gathered and copied to the host")
+                    "Gram / filter / future cost; sigma3 (all-reduce), P3, P3_new; the 900-frame walk on rank 0 over "
+                    "survivor lists read on demand from the owning ranks' shards (peer-mapped)")
     e2e = {"value": n * n / t_e2e, "unit": "frame-pairs/s", "h2d_bytes_per_step": int(host.numel()),
            "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * t_e2e, "includes": includes}
     del host

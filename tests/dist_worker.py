@@ -25,6 +25,7 @@ def main():
     for _ in range(3 if mode == "sym" else 1):          # repeated calls reuse the symmetric buffers (parities, flag epochs)
         res = avd.classic_sharded(frames, fs, stride, rank, world, sigma_factor=f, threshold=th, workspace=ws)
     rowptr, colidx = avd.gather_survivors(res)
+    p_m = res.plan.m
     single = selfcheck.single_gpu_pipeline(frames, fs, stride, f, th)
     pfs = avd.pack_frames_sharded(frames, rank, world)
     assert torch.equal(pfs.sqnorm, single["pf"].sqnorm) and pfs.exact_ok == single["pf"].exact_ok
@@ -36,6 +37,14 @@ def main():
     np.random.seed(0)
     b = texture_walk((rp1, ci1), 1, 30, 5, stride, fs)
     ok["walk"] = a == b
+    if ws is not None:                                   # one-sided lazy rows out of the peers' symmetric P3_new shards
+        ws.barrier(2)
+        if rank == 0:
+            rows = avd.sharded_survivor_rows(res, ws)
+            np.random.seed(0)
+            c = texture_walk(rows, 1, 30, 5, stride, fs)
+            ok["lazy_walk"] = c == b and all(np.array_equal(rows[i], ci1[rp1[i]:rp1[i + 1]]) for i in (0, p_m // 2, p_m - 1))
+        dist.barrier()
     flag = torch.tensor([int(all(ok.values()))], device="cuda")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     p = res.plan

@@ -54,3 +54,22 @@ def test_virtual_ranks_repeated_calls_and_c5_shape():
     """8 ranks on the C5 layout (64x64 frames, -m 3) at a reduced frame count, three calls on the same buffers."""
     res = _check(6000, 64, 64, 40, 4, 8, calls=3)
     assert res[0].plan.m == 1491 and res[0].n_sweeps >= 2
+
+
+def test_lazy_survivor_rows_equal_bulk_csr():
+    """engine.SurvivorRows (per-row device compaction on demand, what the large-N walk uses) == the bulk CSR."""
+    from audio_video_textures_b200 import engine, selfcheck
+    from audio_video_textures_b200.classic.video_textures import texture_walk
+    from audio_video_textures_b200.synth import synth_video
+    frames = synth_video(900, 16, 16, seed=4).cuda()
+    single = selfcheck.single_gpu_pipeline(frames, 40, 1, 4.5, 0.08)
+    rowptr, colidx = engine.csr_from_matrix(single["P3n"], single["counts"])
+    rows = engine.SurvivorRows.from_matrix(single["P3n"])
+    for i in (0, 1, 100, 500, len(rows) - 1):
+        np.testing.assert_array_equal(rows[i], colidx[rowptr[i]:rowptr[i + 1]])
+    for mode in (1, 2, 3):
+        np.random.seed(3)
+        a = texture_walk((rowptr, colidx), mode, 30, 10, 1, 40)
+        np.random.seed(3)
+        b = texture_walk(engine.SurvivorRows.from_matrix(single["P3n"]), mode, 30, 10, 1, 40)
+        assert a == b
