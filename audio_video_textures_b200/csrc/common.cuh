@@ -89,6 +89,22 @@ __device__ __forceinline__ float4 ld_stream_f4(const float *p) {
     return r;
 }
 
+// Coherent, L1-CACHED 128-bit / 32-bit loads (ld.global.ca).  For vectors that other CTAs (or peer GPUs) rewrite
+// between grid barriers: a gpu-scope fence / grid.sync invalidates L1, so lines cached after the barrier are
+// current, and every later reader on the SM hits L1 instead of pulling the same bytes through L2 again
+// (__ldcg made the future-cost sweeps L2-bandwidth bound: two m vectors per D3 element = 3x the D3 bytes
+// through the ~12 TB/s L2 fabric).  Never ld.global.nc here: the non-coherent path may keep stale lines.
+__device__ __forceinline__ float4 ld_ca_f4(const float *p) {
+    float4 r;
+    asm volatile("ld.global.ca.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p) : "memory");
+    return r;
+}
+__device__ __forceinline__ float ld_ca_f(const float *p) {
+    float r;
+    asm volatile("ld.global.ca.f32 %0, [%1];" : "=f"(r) : "l"(p) : "memory");
+    return r;
+}
+
 // x ** p for x >= 0, p > 0 (the future-cost power D2 ** 0.7, classic/q_learning.py:34).
 // powf() costs ~150 instructions per element and made the filter kernel compute-bound.  Here
 // x = 2^e * m (m in [1,2)):  x^p = 2^(p*e) * 2^(p*log2 m).  p is split as p_hi + p_lo with p_hi on

@@ -48,10 +48,10 @@ __device__ __forceinline__ void sweep_vec4(const float4 v, const float *__restri
                                            const float *__restrict__ mp2, int64_t k, int64_t j, float alpha,
                                            SweepAcc &acc) {
     float4 a = make_float4(0.f, 0.f, 0.f, 0.f), a2 = a;
-    // ld.global.cg: the m vectors are rewritten between sweeps by other CTAs of the fused kernel, so they
-    // must come from L2, never from the non-coherent / L1 path
-    if (USE_A) a = __ldcg(reinterpret_cast<const float4 *>(mp + k));
-    if (EPS && HAVE2) a2 = __ldcg(reinterpret_cast<const float4 *>(mp2 + k));
+    // the m vectors are rewritten between sweeps by other CTAs (and peer GPUs) of the fused kernels: coherent
+    // loads, cached in L1 — the grid barrier between sweeps invalidates L1 (see ld_ca_f4)
+    if (USE_A) a = ld_ca_f4(mp + k);
+    if (EPS && HAVE2) a2 = ld_ca_f4(mp2 + k);
     sweep_elem<USE_A, EPS, HAVE2>(v.x, a.x, a2.x, k + 0, j, alpha, acc);
     sweep_elem<USE_A, EPS, HAVE2>(v.y, a.y, a2.y, k + 1, j, alpha, acc);
     sweep_elem<USE_A, EPS, HAVE2>(v.z, a.z, a2.z, k + 2, j, alpha, acc);
@@ -76,7 +76,7 @@ __device__ __forceinline__ void sweep_row(const float *__restrict__ row, int64_t
     }
     for (; k < mv; k += ST * 4) sweep_vec4<USE_A, EPS, HAVE2>(ld_stream_f4(row + k), mp, mp2, k, j, alpha, acc);
     for (int64_t s = mv + threadIdx.x; s < m; s += ST)
-        sweep_elem<USE_A, EPS, HAVE2>(row[s], USE_A ? __ldcg(mp + s) : 0.f, (EPS && HAVE2) ? __ldcg(mp2 + s) : 0.f, s, j, alpha, acc);
+        sweep_elem<USE_A, EPS, HAVE2>(row[s], USE_A ? ld_ca_f(mp + s) : 0.f, (EPS && HAVE2) ? ld_ca_f(mp2 + s) : 0.f, s, j, alpha, acc);
 }
 
 __global__ void __launch_bounds__(ST)

@@ -67,6 +67,21 @@ elif what == "gram5":
     ms, _ = timed(lambda: engine.gram_l2(pf, 0, rows, symmetric=False, out=D), reps=3)
     ops = 2.0 * rows * 100000 * 12288
     print(f"gram5 {rows} x 100000 K=12288: {ms:.3f} ms  {ops / ms / 1e9:.0f} TOP/s")
+elif what == "fc":
+    n = int(sys.argv[2]) if len(sys.argv) > 2 else 20000
+    frames = synth_video_cuda(n, 64, 64, seed=0)
+    pf = engine.pack_frames(frames)
+    D1 = engine.gram_l2(pf)
+    D2, D3 = engine.diag_filter(D1, 40, 1, p=0.7)
+    del D1, D2
+    m = D3.shape[0]
+    ms, fc = timed(lambda: engine.future_cost_fused(D3), reps=3)
+    passes = fc.passes
+    b = 4.0 * m * m * passes
+    print(f"future_cost_fused M={m}: {ms:.3f} ms for {passes} passes = {ms / passes:.3f} ms/pass  {b / ms / 1e6:.0f} GB/s  {b / ms / 1e6 / HBM:.3f} of HBM")
+    ms2, fc2 = timed(lambda: engine.future_cost(D3), reps=2)
+    print(f"future_cost (one launch per sweep, host reads eps) M={m}: {ms2:.3f} ms for {fc2.passes} passes")
+    assert torch.equal(fc.mvec, fc2.mvec[:m]) and fc.n_sweeps == fc2.n_sweeps
 elif what == "synth":
     from audio_video_textures_b200.contrastive.validate import SynthesisState
     L, D = 20000, 2304
