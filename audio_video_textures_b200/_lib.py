@@ -48,6 +48,7 @@ SIGNATURES = {
                              _p, _int, _p, _p, _p, _p, _int, _int, _int, _p],
     "avtex_gram_tile_schedule": [_int, _int, _int, C.POINTER(_int), C.POINTER(_int), _int],
     "avtex_gram_tile_schedule2": [_int, _int, _int, C.POINTER(_int), C.POINTER(_int), _int],
+    "avtex_gram_tile_schedule2g": [_int, _int, _int, _int, C.POINTER(_int), C.POINTER(_int), _int],
 }
 
 class GramJob(C.Structure):

@@ -79,6 +79,7 @@ struct GramArgs {
     unsigned long long *nnz;
     uint32_t idesc;                     // kind::i8 instruction descriptor (signed or unsigned operands)
     int num_jobs, num_tiles;
+    int group_m;                        // schedule group (row-tiles) of the 2-CTA kernel
     unsigned long long *clock_probe;    // nullable: [0] SM cycles, [1] ns spent by CTA 0's first epilogue warp
     GramJob jobs[MAX_JOBS];
 };
@@ -184,7 +185,8 @@ struct EpiStats {
 
 template <typename Release>
 __device__ __forceinline__ void epilogue_tile(const GramArgs &args, const GramJob &job, uint32_t t_base, int64_t r0,
-                                              int64_t c0, int lane, float *tile, Release release, EpiStats &st) {
+                                              int64_t c0, int lane, float *tile, Release release, EpiStats &st,
+                                              int cc_begin = 0, int cc_end = BN / 32) {
     const int64_t row_end = job.row0 + job.rows, col_end = job.col0 + job.cols;
     const int64_t r = r0 + lane;
     const bool r_ok = r < row_end;
@@ -197,10 +199,10 @@ __device__ __forceinline__ void epilogue_tile(const GramArgs &args, const GramJo
     const int w_direct = (job.D != nullptr) ? ((job.DT != nullptr) ? 2 : 1) : 0;
     const int w_trans = (job.D != nullptr) ? 0 : 1;
 #pragma unroll 1
-    for (int cc = 0; cc < BN / 32; ++cc) {
+    for (int cc = cc_begin; cc < cc_end; ++cc) {
         uint32_t g[32];
         tmem_ld32(t_base + cc * 32, g);
-        if (cc == BN / 32 - 1) {                                  // all of this warp's reads are done
+        if (cc == cc_end - 1) {                                   // all of this warp's reads are done
             tc_fence_before();
             __syncwarp();
             if (lane == 0) release();
@@ -458,8 +460,17 @@ gram_l2_s8_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
 constexpr int BM2 = 256;                              // rows per cluster tile
 constexpr int STAGES2 = 6;
 constexpr int STAGE2_BYTES = 2 * A_BYTES;             // A half (128 rows) + B half (128 rows)
-constexpr int GROUP_M2 = 8;
-constexpr int SMEM2_BYTES = STAGES2 * STAGE2_BYTES + 1024 + 256 + EPI_SMEM_BYTES;
+// Row-tiles per schedule group.  A wave of 74 CTA pairs then touches G A-tiles and ~74/G B-tiles; every B tile is
+// re-read once per group of rows, so DRAM reads ~ operand bytes x ceil(TM / G).  8 for long K (a 256-row operand
+// tile is 38 MB at K = 150528: only the current K window of each tile lives in L2 anyway), 16 for K <= 16384
+// (3 MB tiles: 16 + 5 of them fit in L2; measured at K = 12288 with G = 8: 4.2x the operand bytes from DRAM).
+constexpr int GROUP_M2_DEFAULT = 8;
+// 8 epilogue warps (two per TMEM lane quarter, 128 accumulator columns each): with four, one warp per scheduler
+// had to drain 128 x 256 outputs per tile alone, and at K = 12288 (25 us of MMAs per tile) the epilogue, not the
+// tensor pipe, set the tile time (tensor pipe 44-49 % active, L2 35 %: neither memory nor math bound)
+constexpr int EPI_WARPS2 = 8;
+constexpr int NUM_THREADS2 = 64 + 32 * EPI_WARPS2;
+constexpr int SMEM2_BYTES = STAGES2 * STAGE2_BYTES + 1024 + 256 + EPI_WARPS2 * 32 * EPI_PITCH * 4;
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
     uint32_t r;
@@ -508,7 +519,7 @@ __device__ __forceinline__ void umma_s8_2cta(uint32_t tmem_d, uint64_t desc_a, u
 
 // 256 x 256 tiles; symmetric mode keeps (tm, tn) iff tn >= tm.  Groups of GROUP_M2 row-tiles,
 // column-major inside a group (same L2 argument as the 1-CTA schedule).
-__host__ __device__ inline int sym2_group_count(int g, int TM, int TN, int *gm_out) {
+__host__ __device__ inline int sym2_group_count(int g, int TM, int TN, int *gm_out, int GROUP_M2 = GROUP_M2_DEFAULT) {
     const int first = g * GROUP_M2;
     const int gm = (TM - first < GROUP_M2) ? (TM - first) : GROUP_M2;
     int cnt = 0;
@@ -520,7 +531,8 @@ __host__ __device__ inline int sym2_group_count(int g, int TM, int TN, int *gm_o
     return cnt;
 }
 
-__host__ __device__ inline void decode_tile2(int t, int TM, int TN, int symmetric, int *tm, int *tn) {
+__host__ __device__ inline void decode_tile2(int t, int TM, int TN, int symmetric, int *tm, int *tn,
+                                             int GROUP_M2 = GROUP_M2_DEFAULT) {
     if (!symmetric) {
         const int per_group = GROUP_M2 * TN;
         const int g = t / per_group;
@@ -533,7 +545,7 @@ __host__ __device__ inline void decode_tile2(int t, int TM, int TN, int symmetri
     }
     for (int g = 0;; ++g) {
         int gm;
-        const int cnt = sym2_group_count(g, TM, TN, &gm);
+        const int cnt = sym2_group_count(g, TM, TN, &gm, GROUP_M2);
         if (t < cnt) {
             const int first = g * GROUP_M2;
             for (int j = 0; j < GROUP_M2; ++j) {
@@ -550,14 +562,14 @@ __host__ __device__ inline void decode_tile2(int t, int TM, int TN, int symmetri
     }
 }
 
-int count_tiles2(int TM, int TN, int symmetric) {
+int count_tiles2(int TM, int TN, int symmetric, int GROUP_M2 = GROUP_M2_DEFAULT) {
     if (!symmetric) return TM * TN;
     int total = 0, gm;
-    for (int g = 0; g * GROUP_M2 < TM; ++g) total += sym2_group_count(g, TM, TN, &gm);
+    for (int g = 0; g * GROUP_M2 < TM; ++g) total += sym2_group_count(g, TM, TN, &gm, GROUP_M2);
     return total;
 }
 
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS2, 1)
 gram_l2_s8_2cta_kernel(const __grid_constant__ CUtensorMap map, const GramArgs args) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
@@ -577,7 +589,7 @@ gram_l2_s8_2cta_kernel(const __grid_constant__ CUtensorMap map, const GramArgs a
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map) : "memory");
         for (int s = 0; s < STAGES2; ++s) { mbar_init(full_bar + 8 * s, 2); mbar_init(empty_bar + 8 * s, 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar + 8 * s, 1); mbar_init(tempty_bar + 8 * s, 8); }
+        for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar + 8 * s, 1); mbar_init(tempty_bar + 8 * s, 2 * EPI_WARPS2); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) tmem_alloc_2cta(tmem_slot, TMEM_COLS);
@@ -594,7 +606,7 @@ gram_l2_s8_2cta_kernel(const __grid_constant__ CUtensorMap map, const GramArgs a
             for (int t = cluster_id; t < args.num_tiles; t += num_clusters) {
                 int tm, tn, lt;
                 const GramJob &job = args.jobs[find_job(args, t, &lt)];
-                decode_tile2(lt, job.TM, job.TN, job.symmetric, &tm, &tn);
+                decode_tile2(lt, job.TM, job.TN, job.symmetric, &tm, &tn, args.group_m);
                 int row_a = int(job.row0) + tm * BM2 + int(rank) * BM;
                 int row_b = int(job.col0) + tn * BN + int(rank) * (BN / 2);
                 if (row_a >= args.n) row_a = 0;           // fully out-of-range half: load anything, stores are masked
@@ -636,29 +648,31 @@ gram_l2_s8_2cta_kernel(const __grid_constant__ CUtensorMap map, const GramArgs a
             }
         }
     } else {
-        // ===================== epilogue (warps 2..5, both CTAs: own 128 rows) =====================
+        // ===================== epilogue (warps 2..9, both CTAs: own 128 rows) =====================
+        // warp w may read TMEM lanes 32*(w%4)..+31: warps 2-5 take accumulator columns 0..127, warps 6-9 128..255
         const int quarter = warp & 3;
+        const int half = (warp - 2) >> 2;
         float *epi_tile = reinterpret_cast<float *>(smem_raw + (bars + 256 - raw)) + (warp - 2) * 32 * EPI_PITCH;
         int acc = 0;
         uint32_t acc_phase = 0;
         EpiStats st{0.0, 0ull};
         // in-kernel clock probe: SM cycles and wall nanoseconds over this CTA's whole tile loop give the
         // SM clock the kernel actually ran at (NVML's 10 ms samples cannot see a 1 ms kernel)
-        const bool probe = (args.clock_probe != nullptr) && blockIdx.x == 0 && warp == 2 && lane == 0;
+        const bool probe = (args.clock_probe != nullptr) && blockIdx.x == 0 && warp == 2 && lane == 0;   // (one of 8 epilogue warps)
         long long c0 = 0;
         unsigned long long g0 = 0;
         if (probe) { c0 = clock64(); asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g0)); }
         for (int t = cluster_id; t < args.num_tiles; t += num_clusters) {
             int tm, tn, lt;
             const GramJob &job = args.jobs[find_job(args, t, &lt)];
-            decode_tile2(lt, job.TM, job.TN, job.symmetric, &tm, &tn);
+            decode_tile2(lt, job.TM, job.TN, job.symmetric, &tm, &tn, args.group_m);
             mbar_wait(tfull_bar + 8 * acc, acc_phase);
             tc_fence_after();
             const uint32_t t_base = tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(acc * BN);
             const uint32_t release = tempty_bar + 8 * acc;
             epilogue_tile(args, job, t_base, job.row0 + int64_t(tm) * BM2 + int64_t(rank) * BM + quarter * 32,
                           job.col0 + int64_t(tn) * BN, lane, epi_tile,
-                          [release]() { mbar_arrive_cluster(release, 0); }, st);
+                          [release]() { mbar_arrive_cluster(release, 0); }, st, half * (BN / 64), (half + 1) * (BN / 64));
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
         if (probe) {
@@ -729,6 +743,7 @@ int launch_gram_jobs(const void *operand, bool is_signed, int64_t n, int64_t k_e
     a.idesc = make_idesc(bm, is_signed);
     a.num_jobs = num_jobs;
     a.clock_probe = clock_probe;
+    a.group_m = (k_extent <= 16384) ? 16 : GROUP_M2_DEFAULT;
     int total = 0;
     for (int j = 0; j < num_jobs; ++j) {
         const AvtexGramJob &in = jobs[j];
@@ -753,7 +768,7 @@ int launch_gram_jobs(const void *operand, bool is_signed, int64_t n, int64_t k_e
         o.TN = int((in.cols + BN - 1) / BN);
         o.tile_begin = total;
         o.pad_ = 0;
-        total += two_cta ? count_tiles2(o.TM, o.TN, o.symmetric) : count_tiles(o.TM, o.TN, o.symmetric);
+        total += two_cta ? count_tiles2(o.TM, o.TN, o.symmetric, a.group_m) : count_tiles(o.TM, o.TN, o.symmetric);
     }
     a.num_tiles = total;
 
@@ -770,7 +785,7 @@ int launch_gram_jobs(const void *operand, bool is_signed, int64_t n, int64_t k_e
         }
         int clusters = sms / 2;
         if (a.num_tiles < clusters) clusters = a.num_tiles;
-        gram_l2_s8_2cta_kernel<<<2 * clusters, NUM_THREADS, SMEM2_BYTES, as_stream(stream)>>>(map, a);
+        gram_l2_s8_2cta_kernel<<<2 * clusters, NUM_THREADS2, SMEM2_BYTES, as_stream(stream)>>>(map, a);
         AVTEX_LAUNCH_CHECK();
         return 0;
     }
@@ -829,6 +844,14 @@ extern "C" int avtex_gram_tile_schedule2(int TM, int TN, int symmetric, int *tm_
     const int total = count_tiles2(TM, TN, symmetric);
     if (tm_out == nullptr) return total;
     for (int t = 0; t < total && t < capacity; ++t) decode_tile2(t, TM, TN, symmetric, &tm_out[t], &tn_out[t]);
+    return total;
+}
+
+extern "C" int avtex_gram_tile_schedule2g(int TM, int TN, int symmetric, int group, int *tm_out, int *tn_out, int capacity) {
+    if (group < 1 || group > 64) return -1;
+    const int total = count_tiles2(TM, TN, symmetric, group);
+    if (tm_out == nullptr) return total;
+    for (int t = 0; t < total && t < capacity; ++t) decode_tile2(t, TM, TN, symmetric, &tm_out[t], &tn_out[t], group);
     return total;
 }
 

@@ -602,9 +602,15 @@ def audio_start(x: torch.Tensor, d: torch.Tensor) -> int:
     return int(out.item())
 
 
-def gram_tile_schedule(TM: int, TN: int, symmetric: bool, two_cta: bool = False):
+def gram_tile_schedule(TM: int, TN: int, symmetric: bool, two_cta: bool = False, group: int | None = None):
     """Test hook (host only, no GPU): visiting order of the Gram tiles (128x256, or 256x256 for 2-CTA)."""
     lib = _lib.load()
+    if group is not None:
+        total = lib.avtex_gram_tile_schedule2g(TM, TN, 1 if symmetric else 0, group, None, None, 0)
+        tm = (C.c_int * total)()
+        tn = (C.c_int * total)()
+        lib.avtex_gram_tile_schedule2g(TM, TN, 1 if symmetric else 0, group, tm, tn, total)
+        return list(zip(tm, tn))
     fn = lib.avtex_gram_tile_schedule2 if two_cta else lib.avtex_gram_tile_schedule
     total = fn(TM, TN, 1 if symmetric else 0, None, None, 0)
     tm = (C.c_int * total)()

@@ -269,6 +269,8 @@ AVTEX_API int avtex_audio_start(const float *x, int64_t ld, int64_t rows, int64_
 AVTEX_API int avtex_gram_tile_schedule(int TM, int TN, int symmetric, int *tm_out, int *tn_out, int capacity);
 /* Same for the default 2-CTA kernel (256 x 256 tiles; symmetric keeps tn >= tm). */
 AVTEX_API int avtex_gram_tile_schedule2(int TM, int TN, int symmetric, int *tm_out, int *tn_out, int capacity);
+/* ... with an explicit group size (row-tiles per L2 super-tile: 8 for long K, 16 for K <= 16384). */
+AVTEX_API int avtex_gram_tile_schedule2g(int TM, int TN, int symmetric, int group, int *tm_out, int *tn_out, int capacity);
 
 #ifdef __cplusplus
 }

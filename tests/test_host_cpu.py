@@ -134,6 +134,11 @@ def test_gram_tile_schedule_2cta(T):
     assert len(s) == len(set(s)) and set(s) == {(a, b) for a in range(T) for b in range(T) if b >= a}
     s = engine.gram_tile_schedule(max(1, T // 3), T, False, two_cta=True)
     assert sorted(s) == [(a, b) for a in range(max(1, T // 3)) for b in range(T)]
+    for group in (16, 5):                                  # the short-K schedule (16) and an odd size
+        s = engine.gram_tile_schedule(T, T, True, group=group)
+        assert len(s) == len(set(s)) and set(s) == {(a, b) for a in range(T) for b in range(T) if b >= a}
+        s = engine.gram_tile_schedule(max(1, T // 3), T, False, group=group)
+        assert sorted(s) == [(a, b) for a in range(max(1, T // 3)) for b in range(T)]
 
 
 @pytest.mark.parametrize("n,fs,stride,world", [(5000, 40, 4, 8), (300, 40, 1, 2), (100000, 40, 4, 8), (520, 40, 4, 3)])
