@@ -8,10 +8,16 @@
 // issues (R-1)*s + fs loads for R outputs instead of R*fs, and the taps are compile-time indexed
 // kernel parameters (constant-bank FFMA operands: no shared-memory or LDS traffic at all).  Within
 // a warp consecutive threads own consecutive diagonals, so every load is a coalesced row segment.
+//
+// Stride 1 (-m 1 / -m 2) is bound by the FP32 pipe, not by HBM: 40 FMAs per output = 0.32 ms of pure FMA-pipe time
+// at N = 16000 against 0.47 ms of HBM time, plus ~45 instructions per output of loads / pow / stores / statistics;
+// this kernel runs at 89 % issue utilisation there (1.11 ms, 0.42 of the HBM roofline).  Round 2 tried the
+// shared-memory staged sliding-window design the north star names (cp.async ring, one LDS + 20.5 FFMA2 per
+// output, tap pairs in registers; also a warp-specialised form with setmaxnreg): both were correct and
+// bit-identical but SLOWER (1.28 - 1.40 ms) — 124 live tap / accumulator registers leave 12-16 warps per SM and
+// the write-out code dominates; FFMA2 halves issue slots, not FP32-pipe cycles.  The experiment (source, ncu
+// captures, analysis) is kept under profiles/r02_filter_sliding_window_experiment.*; DESIGN.md §4.2.
 #include <stdlib.h>
-
-#include <atomic>
-#include <type_traits>
 
 #include "common.cuh"
 
@@ -119,229 +125,6 @@ diag_filter_kernel(const float *__restrict__ D1, int64_t ld1, int64_t in_row0, i
     }
 }
 
-// ------------------------------------------------------------------ stride 1: sliding window from shared memory
-// At stride 1 every input D1[r, c] feeds FS outputs of its diagonal, so the kernel above (16 outputs per
-// thread, 55 loads, taps re-read from the constant bank) was ISSUE-bound at 0.34 of the HBM roofline.
-// Here a thread walks its diagonal for a whole band of rows with a sliding window: FS/2 + 1 accumulator
-// PAIRS rotate through compile-time register names (the loop body covers one full rotation, FS + 2 inputs),
-// each input is read once from shared memory and contributes through FS/2 + 1 packed fp32x2 FMAs (FFMA2:
-// two outputs per instruction); the tap pairs (w[q], w[q-1]) live in registers for the whole band.  Inputs
-// are staged by cp.async in chunks of CH rows x (128 + CH) columns (6-stage ring, 128-bit, zero-filled
-// outside the matrix), so the loads are decoupled from the FMA stream.  Per output: ~20.5 FFMA2 + 1 LDS
-// instead of 40 FFMA + 3.4 LDG + constant-bank traffic.  The per-output operation order (k ascending
-// fmaf chain from 0) is the same as diag_filter_kernel's, so the two kernels are bit-identical.
-template <int FS>
-struct S1Cfg {
-    static constexpr int PER = FS + 2;                               // inputs per unrolled body
-    static constexpr int NP = PER / 2;                               // accumulator pairs in rotation
-    static constexpr int NCH = 3;                                    // smem chunks per body
-    static constexpr int CH = PER / NCH;                             // rows per chunk
-    static constexpr int PITCH = ((FT + CH + 3 + 3) / 4) * 4;        // floats per staged row
-    static constexpr int VEC_PER_ROW = PITCH / 4;
-    static constexpr int CHUNK_VECS = CH * VEC_PER_ROW;
-    static constexpr int STAGES = 6;
-    static constexpr int IN_BYTES = STAGES * CH * PITCH * 4;
-    static constexpr int SMEM_BYTES = IN_BYTES + CH * FT * 4;        // + per-thread output staging [CH][FT]
-    static_assert(FS % 2 == 0 && PER % NCH == 0, "sliding-window filter needs FS even and (FS + 2) % 3 == 0");
-};
-
-__device__ __forceinline__ void cp_async16_zfill(uint32_t dst, const void *src, int bytes) {
-    // copies `bytes` (0..16) from src and zero-fills the rest of the 16 destination bytes
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-
-template <int FS, bool STATS, bool POW>
-__global__ void __launch_bounds__(FT, 3)
-diag_filter_s1_kernel(const float *__restrict__ D1, int64_t ld1, int64_t in_row0, int64_t in_rows, const Taps64 taps,
-                      int64_t a0, int64_t rows_out, int64_t m, float *__restrict__ D2, int64_t ld2,
-                      float *__restrict__ D3, int64_t ld3, float p, double *sum, unsigned long long *nnz, int nb) {
-    using C = S1Cfg<FS>;
-#ifndef AVTEX_S1_UR_PAIRS
-#define AVTEX_S1_UR_PAIRS 0
-#endif
-    constexpr int UR_PAIRS = AVTEX_S1_UR_PAIRS < FS + 1 ? AVTEX_S1_UR_PAIRS : FS + 1;
-    constexpr int KV = (C::CHUNK_VECS + FT - 1) / FT;                 // 128-bit copies per thread per chunk
-    extern __shared__ __align__(16) float s1_smem[];
-    __shared__ double sred[32];
-    __shared__ unsigned long long nred[32];
-    __shared__ float2 wp_s[FS + 1];
-    const int64_t n_in = m - 1 + FS;                                  // valid input rows / cols (stride 1)
-    const int band = C::PER * nb - FS;                                // output rows per band
-    const int64_t a_band = a0 + int64_t(blockIdx.y) * band;
-    const int64_t c_blk = int64_t(blockIdx.x) * FT - (band - 1);      // output column of thread 0 at i = 0
-    const int64_t c_thread = c_blk + threadIdx.x;
-    const int64_t row_lim = (in_row0 + in_rows < n_in) ? in_row0 + in_rows : n_in;
-    const int total_chunks = nb * C::NCH;
-    const uint32_t smem_base = static_cast<uint32_t>(__cvta_generic_to_shared(s1_smem));
-
-    // ---- staging: chunk j = input rows [a_band + j*CH, +CH) x columns [cb, cb + PITCH), cb = (c_blk + j*CH) & ~3.
-    // The (row, column) a thread copies inside a chunk never changes, only the chunk origin does.
-    uint32_t v_soff[KV];
-    int64_t v_goff[KV];
-#pragma unroll
-    for (int k = 0; k < KV; ++k) {
-        const int v = threadIdx.x + k * FT;
-        const int rr = v / C::VEC_PER_ROW, cc = (v - rr * C::VEC_PER_ROW) * 4;
-        v_soff[k] = uint32_t(rr * C::PITCH + cc) * 4u;
-        v_goff[k] = int64_t(rr) * ld1 + cc;
-    }
-    auto issue_chunk = [&](int j) {
-        if (j < total_chunks) {
-            const int64_t r0 = a_band + int64_t(j) * C::CH;
-            const int64_t cb = (c_blk + int64_t(j) * C::CH) & ~int64_t(3);
-            const uint32_t dst0 = smem_base + uint32_t(j % C::STAGES) * (C::CH * C::PITCH * 4);
-            const float *base = D1 + (r0 - in_row0) * ld1 + cb;
-            if (r0 + C::CH <= row_lim && cb >= 0 && cb + C::PITCH <= n_in) {     // CTA-uniform: the whole chunk is inside
-#pragma unroll
-                for (int k = 0; k < KV; ++k)
-                    if (k < KV - 1 || threadIdx.x + k * FT < C::CHUNK_VECS)
-                        cp_async16_zfill(dst0 + v_soff[k], base + v_goff[k], 16);
-            } else {
-#pragma unroll
-                for (int k = 0; k < KV; ++k)
-                    if (k < KV - 1 || threadIdx.x + k * FT < C::CHUNK_VECS) {
-                        // bytes beyond the copied prefix are ZERO-filled: rows past the block, columns < 0 and
-                        // columns >= n_in (row padding may hold NaN bit patterns, and 0 * NaN would poison a valid
-                        // output through the zero half of an edge tap pair)
-                        const int v = threadIdx.x + k * FT;
-                        const int rr = v / C::VEC_PER_ROW, cc = (v - rr * C::VEC_PER_ROW) * 4;
-                        const int64_t r = r0 + rr, c = cb + cc;
-                        int64_t cnt = (r < row_lim && c >= 0) ? n_in - c : 0;
-                        cnt = cnt < 0 ? 0 : (cnt > 4 ? 4 : cnt);
-                        cp_async16_zfill(dst0 + v_soff[k], cnt > 0 ? base + v_goff[k] : D1, int(cnt) * 4);
-                    }
-            }
-        }
-        cp_async_commit();                                             // empty groups keep the wait count uniform
-    };
-#pragma unroll
-    for (int j = 0; j < C::STAGES - 1; ++j) issue_chunk(j);
-
-    // ---- tap pairs (w[q], w[q-1]), q = 0..FS, held in REGISTERS for the whole band.  They are read back from
-    // shared memory on purpose: values ptxas can trace to the constant bank get rematerialised into uniform
-    // registers at every use (63 URs for 82 values), which cost more issue slots than the packing saved.
-    if (threadIdx.x <= FS) {
-        const int q = threadIdx.x;
-        wp_s[q] = make_float2(q < FS ? taps.w[q] : 0.f, q >= 1 ? taps.w[q - 1] : 0.f);
-    }
-    __syncthreads();
-    float2 wp[FS + 1];
-#pragma unroll
-    for (int q = 0; q <= FS; ++q) {
-        if (q < UR_PAIRS) {            // constant-bank values: ptxas keeps these pairs in UNIFORM registers (no vector registers)
-            wp[q] = make_float2(q < FS ? taps.w[q] : 0.f, q >= 1 ? taps.w[q - 1] : 0.f);
-        } else {
-            wp[q].x = *reinterpret_cast<volatile float *>(&wp_s[q].x);
-            wp[q].y = *reinterpret_cast<volatile float *>(&wp_s[q].y);
-        }
-    }
-    float2 acc[C::NP];
-#pragma unroll
-    for (int sidx = 0; sidx < C::NP; ++sidx) acc[sidx] = make_float2(0.f, 0.f);
-
-    // ---- outputs: local index i <-> (a_band + i, c_thread + i); valid i in [i_lo, i_lo + i_span).  The pair
-    // completed at input step t holds outputs i = t - FS and t - FS + 1.  Completed values are parked in a
-    // per-thread column of shared memory (compile-time offsets) and written out by a small ROLLED loop after each
-    // chunk: predicate, D2 store, pow, D3 store and the sigma statistics exist once in the code and their
-    // addresses advance by ld + 1 per output (the fully unrolled form re-derived every address with 64-bit
-    // multiplies and re-read the parameters: ~45 instructions per pair, measured).
-    const int64_t lim_i = ((a0 + rows_out < a_band + band) ? a0 + rows_out : a_band + band) - a_band;
-    const int64_t lo64 = c_thread < 0 ? -c_thread : 0, hi64 = (m - c_thread < lim_i) ? m - c_thread : lim_i;
-    const int i_lo = int(lo64);
-    const unsigned i_span = hi64 > lo64 ? unsigned(hi64 - lo64) : 0u;
-    const int64_t step2 = ld2 + 1, step3 = ld3 + 1;
-    float *o2 = D2 + (a_band - a0) * ld2 + c_thread - int64_t(FS) * step2;     // i = -FS (never dereferenced while invalid)
-    float *o3 = POW ? D3 + (a_band - a0) * ld3 + c_thread - int64_t(FS) * step3 : nullptr;
-    float *out_s = s1_smem + C::IN_BYTES / 4 + threadIdx.x;                     // out_s[r * FT]: my value of chunk row r
-    int i0 = -FS;
-    double s = 0.0;
-    int z = 0;
-
-#pragma unroll 1
-    for (int body = 0; body < nb; ++body) {
-        float fs = 0.f;
-#pragma unroll
-        for (int ch = 0; ch < C::NCH; ++ch) {
-            const int j = body * C::NCH + ch;
-            cp_async_wait<C::STAGES - 2>();                            // chunk j has landed (this thread's part)
-            __syncthreads();                                           // ... everyone's part; chunk j-1 is fully consumed
-            issue_chunk(j + C::STAGES - 1);                            // refill the stage chunk j-1 occupied
-            const int off = int((c_blk + int64_t(j) * C::CH) & 3);
-            const float *rowp = s1_smem + (j % C::STAGES) * (C::CH * C::PITCH) + threadIdx.x + off;
-#pragma unroll
-            for (int r = 0; r < C::CH; ++r) {
-                const int tb = ch * C::CH + r;                         // compile-time step inside the body
-                const float x = rowp[r * C::PITCH + r];
-                const float2 x2 = make_float2(x, x);
-#pragma unroll
-                for (int sidx = 0; sidx < C::NP; ++sidx) {
-                    const int q = (tb - 2 * sidx + 2 * C::PER) % C::PER;          // tap-pair index for slot sidx at this step
-                    if (q <= FS) acc[sidx] = __ffma2_rn(wp[q], x2, acc[sidx]);
-                    if (q == FS) {                                     // slot complete: rows r and r + 1 of this chunk's outputs
-                        static_assert(C::CH % 2 == 0, "pairs must not straddle chunks");
-                        out_s[r * FT] = acc[sidx].x;
-                        out_s[(r + 1) * FT] = acc[sidx].y;
-                        acc[sidx] = make_float2(0.f, 0.f);
-                    }
-                }
-            }
-#pragma unroll 2
-            for (int r = 0; r < C::CH; ++r) {
-                const float v = out_s[r * FT];
-                if (unsigned(i0 - i_lo) < i_span) {
-                    *o2 = v;
-                    if (POW) *o3 = pow_pos(v, p);
-                    if (STATS) { fs += v; z += (v != 0.f); }
-                }
-                o2 += step2;
-                if (POW) o3 += step3;
-                ++i0;
-            }
-        }
-        s += (double)fs;
-    }
-    cp_async_wait<0>();
-    if (STATS) {
-        const double sd = block_reduce(s, 0.0, OpAdd<double>(), sred);
-        const unsigned long long zd = block_reduce((unsigned long long)z, 0ull, OpAdd<unsigned long long>(), nred);
-        if (threadIdx.x == 0) { atomicAdd(sum, sd); atomicAdd(nnz, zd); }
-    }
-}
-
-template <int FS>
-int launch_s1(const float *D1, int64_t ld1, int64_t in_row0, int64_t in_rows, const float *h_w, int64_t a0,
-              int64_t rows_out, int64_t m, float *D2, int64_t ld2, float *D3, int64_t ld3, float p, double *sum,
-              unsigned long long *nnz, int device, cudaStream_t st) {
-    using C = S1Cfg<FS>;
-    Taps64 taps;
-    for (int i = 0; i < 64; ++i) taps.w[i] = (i < FS) ? h_w[i] : 0.f;
-    static std::atomic<bool> attr_set[64];
-    if (device < 0 || device >= 64 || !attr_set[device].load(std::memory_order_acquire)) {
-        AVTEX_CUDA(cudaFuncSetAttribute(diag_filter_s1_kernel<FS, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-        AVTEX_CUDA(cudaFuncSetAttribute(diag_filter_s1_kernel<FS, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-        AVTEX_CUDA(cudaFuncSetAttribute(diag_filter_s1_kernel<FS, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-        AVTEX_CUDA(cudaFuncSetAttribute(diag_filter_s1_kernel<FS, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-        if (device >= 0 && device < 64) attr_set[device].store(true, std::memory_order_release);
-    }
-    // bodies per thread: long bands amortise the FS-1 warm-up rows (band / (band + FS)), short ones keep enough
-    // CTAs in flight on small matrices
-    int64_t nb = (rows_out / 6 + FS + C::PER - 1) / C::PER;
-    if (nb < 2) nb = 2;
-    if (nb > 12) nb = 12;
-    const int64_t band = int64_t(C::PER) * nb - FS;
-    dim3 grid((unsigned)((m + band - 1 + FT - 1) / FT), (unsigned)((rows_out + band - 1) / band));
-#define AVTEX_S1(ST_, PW_)                                                                                          \
-    diag_filter_s1_kernel<FS, ST_, PW_><<<grid, FT, C::SMEM_BYTES, st>>>(D1, ld1, in_row0, in_rows, taps, a0, rows_out, m, \
-                                                                         D2, ld2, D3, ld3, p, sum, nnz, (int)nb)
-    if (sum != nullptr) { if (D3 != nullptr) AVTEX_S1(true, true); else AVTEX_S1(true, false); }
-    else { if (D3 != nullptr) AVTEX_S1(false, true); else AVTEX_S1(false, false); }
-#undef AVTEX_S1
-    return 0;
-}
-
 // Any (fs, stride): one output per thread, taps read from the parameter bank with a runtime index.
 __global__ void __launch_bounds__(FT)
 diag_filter_generic_kernel(const float *__restrict__ D1, int64_t ld1, int64_t in_row0, const TapsBig taps,
@@ -439,17 +222,6 @@ extern "C" int avtex_diag_filter_pow(const float *D1, int64_t ld1, int64_t in_ro
     AVTEX_REQUIRE((sum == nullptr) == (nnz == nullptr), "diag_filter: sum and nnz go together");
     AVTEX_REQUIRE(D3 == nullptr || ld3 >= m, "diag_filter: ld3 too small");
     cudaStream_t st = as_stream(stream);
-    {
-        static const bool s1_off = []() { const char *e = getenv("AVTEX_FILTER_S1"); return e != nullptr && e[0] == '0'; }();
-        const bool aligned = (ld1 % 4 == 0) && ((reinterpret_cast<uintptr_t>(D1) & 15) == 0);
-        if (stride == 1 && aligned && !s1_off && (fs == 40 || fs == 16)) {
-            int rc = fs == 40 ? launch_s1<40>(D1, ld1, in_row0, in_rows, h_w, a0, rows_out, m, D2, ld2, D3, ld3, p, sum, nnz, device, st)
-                              : launch_s1<16>(D1, ld1, in_row0, in_rows, h_w, a0, rows_out, m, D2, ld2, D3, ld3, p, sum, nnz, device, st);
-            if (rc) return rc;
-            AVTEX_LAUNCH_CHECK();
-            return 0;
-        }
-    }
     const int key = fs * 100 + stride;
 #define AVTEX_FAST(FS_, S_)                                                                            \
     case FS_ * 100 + S_:                                                                               \
