@@ -68,13 +68,22 @@ def core_rows(plans: list, r: int, stride: int):
     return p.a0 * stride, (p.n if r == p.world - 1 else p.a1 * stride)
 
 
-def pair_split(lo: int, hi: int) -> int:
+def pair_split(lo: int, hi: int, big_first: bool = True) -> int:
     """Column split point of core_j for the pair (i < j): rank i computes core_i x [lo, mid) and rank j
     computes [mid, hi) x core_i, each pushing the transpose to the other, so both do half of the rectangle
-    whatever the number of ranks.  Aligned to the 256-wide tile."""
-    mid = lo + (hi - lo) // 2
-    mid = lo + (mid - lo + 255) // 256 * 256
-    return min(mid, hi)
+    whatever the number of ranks.  Aligned to the 256-wide tile; `big_first` says which side takes the larger
+    part when the range is not a multiple of two tiles (alternated over the pairs so that no rank collects all
+    the larger halves: with the split always rounded up, rank 0 of 8 did 224 tiles and rank 7 175)."""
+    half = (hi - lo) // 2
+    up = min(hi, lo + (half + 255) // 256 * 256)
+    if -(-(up - lo) // 256) == -(-(hi - up) // 256):       # rounding up already gives both sides the same tile count
+        return up
+    mid = up if big_first else lo + half // 256 * 256
+    return max(lo, min(mid, hi))
+
+
+def _big_first(i: int, j: int) -> bool:
+    return (i + j) % 2 == 1
 
 
 def symmetric_jobs(plans: list, me: int, ptrs: list, ld: int, stride: int) -> list:
@@ -93,12 +102,12 @@ def symmetric_jobs(plans: list, me: int, ptrs: list, ld: int, stride: int) -> li
         olo, ohi = core_rows(plans, other, stride)
         peer = dict(DT=ptrs[other], dt_row0=plans[other].r_lo, ldt=ld)
         if me < other:                                  # my rows x the first half of the peer's columns
-            mid = pair_split(olo, ohi)
+            mid = pair_split(olo, ohi, _big_first(me, other))
             if mid > olo:
                 out.append(dict(row0=lo, rows=hi - lo, col0=olo, cols=mid - olo, symmetric=0, count_stats=1,
                                 **peer, **mine))
         else:                                           # the second half of my rows x the peer's columns
-            mid = pair_split(lo, hi)
+            mid = pair_split(lo, hi, _big_first(other, me))
             if hi > mid:
                 out.append(dict(row0=mid, rows=hi - mid, col0=olo, cols=ohi - olo, symmetric=0, count_stats=1,
                                 **peer, **mine))
