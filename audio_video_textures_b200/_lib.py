@@ -44,6 +44,9 @@ SIGNATURES = {
     "avtex_cosine_scores": [_p, _i64, _i64, _i64, _p, _f32, _p, _int, _p],
     "avtex_select_step": [_p, _p, _i64, _i64, _f32, _f32, _f32, _p, _p, _p, _int, _p],
     "avtex_audio_start": [_p, _i64, _i64, _i64, _p, _p, _p, _int, _p],
+    "avtex_synthesis_loop": [_p, _i64, _i64, _i64, _p, _i64, _p, _i64, _i64, _p, _i64, _f32, _f32, _f32, _f32, _i64, _int,
+                             _p, _p, _p, _p, _p, _p, _p, _p, _int, _p],
+    "avtex_mt19937_randint_host": [_p, C.POINTER(_int), _p, _int, _p],
     "avtex_synthesis_step": [_p, _i64, _i64, _i64, _p, _p, _i64, _i64, _p, _f32, _i64, _f32, _f32, _f32, _p, _p, _p,
                              _p, _int, _p, _p, _p, _p, _int, _int, _int, _p],
     "avtex_gram_tile_schedule": [_int, _int, _int, C.POINTER(_int), C.POINTER(_int), _int],

@@ -73,11 +73,25 @@ class SynthesisState:
                                      self.vals if want_vals else None)
 
 
+def planned_steps(max_length, window: int, stride: int, subsample_rate: int = 1, max_steps=None) -> int:
+    """Number of iterations of `while len(new_frames) < max_length` (cvt/validate.py:324): the first step emits
+    `window` frames, every later one `stride` (validate.py:581-612), whatever is chosen — so the trip count is
+    known before the loop starts, which is what lets the whole loop run on the device."""
+    n_frames, steps = 0, 0
+    while n_frames < max_length and (max_steps is None or steps < max_steps):
+        n_frames += (window if steps == 0 else stride) * subsample_rate
+        steps += 1
+    return steps
+
+
 def synthesize(t_emb, temp=0.1, threshold=0.0, fps=30, new_video_length=30, window=20, stride=4,
                q_start=None, alpha=0.5, mini_batchsize=150, q_emb=None, q_audio=None, t_audio=None,
-               da_source=None, da_driving=None, subsample_rate=1, max_steps=None):
+               da_source=None, da_driving=None, subsample_rate=1, max_steps=None, device_loop=True):
     """Runs the synthesis loop.  Tensors are CUDA (or are moved there).  Consumes the numpy global RNG
-    once per step.  Returns dict(q_ids, frame_ids, jump_count, nz_counts, start)."""
+    once per step — with `device_loop` (default) ON THE DEVICE, inside one persistent kernel, from numpy's own
+    generator state, which is handed back afterwards (engine.synthesis_loop); `device_loop=False` keeps one
+    launch per step with the draw on the host.  Both give the same sequence.
+    Returns dict(q_ids, frame_ids, jump_count, nz_counts, start)."""
     dev = t_emb.device if t_emb.is_cuda else torch.device("cuda")
     mv = lambda x: None if x is None else x.to(dev)
     st = SynthesisState(mv(t_emb), mv(q_emb), mv(q_audio), mv(t_audio), mv(da_source), mv(da_driving))
@@ -89,10 +103,19 @@ def synthesize(t_emb, temp=0.1, threshold=0.0, fps=30, new_video_length=30, wind
         max_length = min(max_length, np.ceil(fps) * np.floor(len(da_driving) * S + W))
     q_id, p_q_id, iter_count, n_frames, jump_count = q_start, -1, 1, 0, 0
     q_ids, frame_ids, nz_counts = [], [], []
+    chosen = None
+    if device_loop:
+        n_steps = planned_steps(max_length, W, S, subsample_rate, max_steps)
+        if n_steps > 0:
+            chosen, nz = engine.synthesis_loop(st.ws, st.tn, st.qn, q_start, n_steps, temp, alpha, threshold, st.sn, st.dn)
     while n_frames < max_length and (max_steps is None or len(q_ids) < max_steps):
-        choices = st.step(q_id, iter_count, temp, alpha, threshold)
-        nz_counts.append(len(choices))
-        q_id = int(np.random.choice(choices))                       # validate.py:570-572
+        if chosen is not None:
+            nz_counts.append(int(nz[len(q_ids)]))
+            q_id = int(chosen[len(q_ids)])
+        else:
+            choices = st.step(q_id, iter_count, temp, alpha, threshold)
+            nz_counts.append(len(choices))
+            q_id = int(np.random.choice(choices))                   # validate.py:570-572
         if p_q_id == -1:                                            # validate.py:581-612
             diff = range(q_id * S, q_id * S + W)
         else:

@@ -9,6 +9,7 @@
 // over survivors; both are reproduced, not corrected.
 #include <cooperative_groups.h>
 #include <float.h>
+#include <string.h>
 
 #include "common.cuh"
 
@@ -221,12 +222,12 @@ __device__ __forceinline__ float warp_row_dot(const float *__restrict__ row, con
 // Selection over the L logits by ONE CTA of SELT threads (the last CTA of the step to finish its rows):
 // mixed values + max, survivor sum, ordered compaction.  Each warp owns a contiguous slice of windows, so the
 // ordered compaction needs one prefix over 32 warp counts instead of a barrier per 1024 elements.
-__device__ void synthesis_select(const SynthStepArgs &p, double *acc) {
+__device__ void synthesis_select(const SynthStepArgs &p, double *acc, int64_t q, int seq) {
     __shared__ double dred[32];
     __shared__ float fred[32];
     __shared__ int wcnt[32];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
-    const int64_t L = p.L, q = p.q;
+    const int64_t L = p.L;
     const int64_t pos = (q + 1 < L - 1) ? q + 1 : L - 1;
     const bool q_in_list = (q == L - 1);
     const bool audio = (p.sn != nullptr);
@@ -290,61 +291,169 @@ __device__ void synthesis_select(const SynthStepArgs &p, double *acc) {
         }
         base += __popc(bal);
     }
+    if (p.host == nullptr) {                                           // device-resident loop: the list stays here
+        __threadfence();
+        __syncthreads();
+        return;
+    }
     // publish: the list, then the count, then the sequence word the host polls
     __threadfence_system();
     __syncthreads();
     if (threadIdx.x == 0) {
         p.host[1] = total;
         __threadfence_system();
-        p.host[0] = p.seq;
+        p.host[0] = seq;
     }
 }
 
-__global__ void __launch_bounds__(SELT)
-synthesis_step_kernel(const SynthStepArgs p) {
-    __shared__ double dred[32];
-    __shared__ int last_s;
+// Logits of one query against all L windows (+ audio logits) and their plain sums over the target list, by all
+// CTAs.  CTA c owns the contiguous rows [c*L/G, (c+1)*L/G); inside the CTA the warps take rows from a SHARED-memory
+// ticket, one at a time: a static warp assignment leaves a 4-or-5 rows split (16 % idle), and a single global
+// ticket serialises on one L2 atomic unit (20000 same-address atomics = the whole 60 us of the first version).
+// Same operation order per row as cosine_scores_kernel.  Adds this CTA's sums to acc[0], acc[1].
+__device__ __forceinline__ void synthesis_scores(const SynthStepArgs &p, const float *qn, const float *dn, int64_t q,
+                                                 double *acc, int *ticket_s, double *dred) {
     const int lane = threadIdx.x & 31;
-    const int64_t L = p.L, q = p.q;
+    const int64_t L = p.L;
     const bool q_in_list = (q == L - 1);
-    double *acc = p.acc + 4 * p.parity, *acc_next = p.acc + 4 * (1 - p.parity);
-    unsigned int *ctr = p.mx + 2 * p.parity, *ctr_next = p.mx + 2 * (1 - p.parity);   // [0] row counter, [1] CTA ticket
     const bool audio = (p.sn != nullptr);
-    if (blockIdx.x == 0 && threadIdx.x < 4) {                          // the other parity's scratch is idle: re-arm it
-        acc_next[threadIdx.x] = 0.0;
-        if (threadIdx.x < 2) ctr_next[threadIdx.x] = 0u;
-    }
-    // ---- logits (same operation order as cosine_scores_kernel) + their plain sums over the target list.
-    // Rows are handed out dynamically, one per warp at a time: 20000 rows over 4736 resident warps would leave a
-    // 4-or-5 split (16 % idle) with a static assignment.
+    const int64_t lo = L * blockIdx.x / gridDim.x, hi = L * (blockIdx.x + 1) / gridDim.x;
+    if (threadIdx.x == 0) *ticket_s = 0;
+    __syncthreads();
     double so = 0.0, sa = 0.0;
-    unsigned int next32 = 0;
-    if (lane == 0) next32 = atomicAdd(ctr, 1u);
+    int next = 0;
+    if (lane == 0) next = atomicAdd(ticket_s, 1);
     for (;;) {
-        const int64_t w = __shfl_sync(0xffffffffu, next32, 0);
-        if (w >= L) break;
-        if (lane == 0) next32 = atomicAdd(ctr, 1u);                    // the next row's ticket travels under this row's loads
-        const float dot = warp_row_dot(p.tn + w * p.ld, p.qn, p.dim, lane);
+        const int64_t w = lo + __shfl_sync(0xffffffffu, next, 0);
+        if (w >= hi) break;
+        if (lane == 0) next = atomicAdd(ticket_s, 1);                  // the next ticket travels under this row's loads
+        const float dot = warp_row_dot(p.tn + w * p.ld, qn, p.dim, lane);
         float ov = 0.f, av = 0.f;
         if (lane == 0) { ov = __fdiv_rn(dot, p.temp); p.o[w] = ov; }
         if (audio) {
-            const float da = warp_row_dot(p.sn + w * p.lds, p.dn, p.dimA, lane);
+            const float da = warp_row_dot(p.sn + w * p.lds, dn, p.dimA, lane);
             if (lane == 0) { av = __fdiv_rn(da, p.temp); p.a[w] = av; }
         }
         if (lane == 0 && !(w == q && !q_in_list)) { so += (double)ov; sa += (double)av; }
     }
     so = block_reduce(so, 0.0, OpAdd<double>(), dred);
     sa = block_reduce(sa, 0.0, OpAdd<double>(), dred);
+    if (threadIdx.x == 0) { atomicAdd(acc + 0, so); atomicAdd(acc + 1, sa); }
+}
+
+__global__ void __launch_bounds__(SELT)
+synthesis_step_kernel(const SynthStepArgs p) {
+    __shared__ double dred[32];
+    __shared__ int ticket_s;
+    __shared__ int last_s;
+    double *acc = p.acc + 4 * p.parity, *acc_next = p.acc + 4 * (1 - p.parity);
+    unsigned int *ctr = p.mx + 2 * p.parity, *ctr_next = p.mx + 2 * (1 - p.parity);   // [1]: CTA ticket
+    if (blockIdx.x == 0 && threadIdx.x < 4) {                          // the other parity's scratch is idle: re-arm it
+        acc_next[threadIdx.x] = 0.0;
+        if (threadIdx.x < 2) ctr_next[threadIdx.x] = 0u;
+    }
+    synthesis_scores(p, p.qn, p.dn, p.q, acc, &ticket_s, dred);
     if (threadIdx.x == 0) {
-        atomicAdd(acc + 0, so);
-        atomicAdd(acc + 1, sa);
         __threadfence();                                               // my rows' logits + sums before my ticket
         last_s = (atomicAdd(ctr + 1, 1u) == gridDim.x - 1);
     }
     __syncthreads();
     if (!last_s) return;
     __threadfence();                                                   // acquire side of the ticket
-    synthesis_select(p, acc);
+    synthesis_select(p, acc, p.q, p.seq);
+}
+
+// ------------------------------------------------------------------ the WHOLE synthesis loop in one launch
+// numpy's legacy generator on the device.  The reference draws the next window with `np.random.choice(choices)`
+// (cvt/validate.py:570) = RandomState.randint(0, n) = one masked-rejection draw of MT19937 32-bit outputs
+// (numpy/random/src/distributions: random_bounded_uint64_fill with use_masked; n == 1 consumes nothing).  With
+// the generator state imported from np.random.get_state() and exported back afterwards, the device draws the
+// SAME numbers the host would have, so the chosen sequence stays bit-identical to the reference while the host
+// leaves the loop entirely: no launch, no copy and no poll per step.
+struct Mt19937 {
+    uint32_t key[624];
+    int pos;
+};
+__host__ __device__ inline void mt19937_gen(Mt19937 *st) {
+    const uint32_t UPPER = 0x80000000u, LOWER = 0x7fffffffu, MATRIX = 0x9908b0dfu;
+    uint32_t *mt = st->key;
+    int kk;
+    uint32_t y;
+    for (kk = 0; kk < 624 - 397; ++kk) {
+        y = (mt[kk] & UPPER) | (mt[kk + 1] & LOWER);
+        mt[kk] = mt[kk + 397] ^ (y >> 1) ^ ((y & 1u) ? MATRIX : 0u);
+    }
+    for (; kk < 623; ++kk) {
+        y = (mt[kk] & UPPER) | (mt[kk + 1] & LOWER);
+        mt[kk] = mt[kk + (397 - 624)] ^ (y >> 1) ^ ((y & 1u) ? MATRIX : 0u);
+    }
+    y = (mt[623] & UPPER) | (mt[0] & LOWER);
+    mt[623] = mt[396] ^ (y >> 1) ^ ((y & 1u) ? MATRIX : 0u);
+    st->pos = 0;
+}
+__host__ __device__ inline uint32_t mt19937_next32(Mt19937 *st) {
+    if (st->pos >= 624) mt19937_gen(st);
+    uint32_t y = st->key[st->pos++];
+    y ^= (y >> 11);
+    y ^= (y << 7) & 0x9d2c5680u;
+    y ^= (y << 15) & 0xefc60000u;
+    y ^= (y >> 18);
+    return y;
+}
+// RandomState.randint(0, n), n >= 1, n - 1 < 2^32 (numpy legacy: masked rejection on 32-bit draws)
+__host__ __device__ inline uint32_t legacy_randint(Mt19937 *st, uint32_t n) {
+    const uint32_t rng = n - 1u;
+    if (rng == 0u) return 0u;
+    if (rng == 0xFFFFFFFFu) return mt19937_next32(st);
+    uint32_t mask = rng;
+    mask |= mask >> 1; mask |= mask >> 2; mask |= mask >> 4; mask |= mask >> 8; mask |= mask >> 16;
+    uint32_t val;
+    do { val = mt19937_next32(st) & mask; } while (val > rng);
+    return val;
+}
+
+struct SynthLoopArgs {
+    SynthStepArgs s;                               // tables, scratch (qn / dn / q / seq / parity unused)
+    const float *qn_table; int64_t ldq;            // normalised query table [L, dim]
+    const float *dn_table; int64_t ldd;            // normalised driving table [>= n_steps + 1, dimA] (nullable)
+    int64_t q_start;
+    int n_steps;
+    Mt19937 *mt;                                   // device copy of numpy's generator state (in / out)
+    int *q_ids, *nz;                               // [n_steps] out
+    int64_t *q_cur;                                // device scalar: the current query (scratch)
+};
+
+__global__ void __launch_bounds__(SELT)
+synthesis_loop_kernel(const SynthLoopArgs a) {
+    __shared__ double dred[32];
+    __shared__ int ticket_s;
+    cg::grid_group grid = cg::this_grid();
+    SynthStepArgs p = a.s;
+    p.host_cap = 0;                                                    // nothing goes to the host during the loop
+    p.host = nullptr;
+    int64_t q = a.q_start;
+    for (int step = 0; step < a.n_steps; ++step) {
+        const int parity = step & 1;
+        double *acc = p.acc + 4 * parity, *acc_next = p.acc + 4 * (1 - parity);
+        if (blockIdx.x == 0 && threadIdx.x < 4) acc_next[threadIdx.x] = 0.0;
+        // driving-audio example `iter_count` = step + 1 (cvt/validate.py:417)
+        const float *dn = a.dn_table != nullptr ? a.dn_table + int64_t(step + 1) * a.ldd : nullptr;
+        synthesis_scores(p, a.qn_table + q * a.ldq, dn, q, acc, &ticket_s, dred);
+        grid.sync();
+        if (blockIdx.x == 0) {
+            synthesis_select(p, acc, q, 0);
+            if (threadIdx.x == 0) {
+                const int n = *p.n_choices;
+                const uint32_t r = legacy_randint(a.mt, (uint32_t)n);  // == np.random.choice(choices)
+                const int64_t nq = p.choices[r];
+                a.q_ids[step] = (int)nq;
+                a.nz[step] = n;
+                *a.q_cur = nq;
+            }
+        }
+        grid.sync();
+        q = *reinterpret_cast<volatile int64_t *>(a.q_cur);
+    }
 }
 
 // sims[w] = <x_w, d> / (||x_w|| * ||d||)   (fp64 accumulation), one warp per row.
@@ -446,6 +555,61 @@ extern "C" int avtex_synthesis_step(const float *tn, int64_t ld, int64_t L, int6
     p.host = host_out; p.host_cap = host_cap; p.seq = seq; p.parity = seq & 1;
     synthesis_step_kernel<<<(unsigned)grid, SELT, 0, as_stream(stream)>>>(p);
     AVTEX_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int avtex_synthesis_loop(const float *tn, int64_t ld, int64_t L, int64_t dim, const float *qn_table,
+                                    int64_t ldq, const float *sn, int64_t lds, int64_t dimA, const float *dn_table,
+                                    int64_t ldd, float temp, float alpha, float one_minus_alpha, float th,
+                                    int64_t q_start, int n_steps, float *ws_f32, double *ws_acc, int *choices,
+                                    int *n_choices, void *mt_state, int64_t *q_scratch, int *q_ids, int *nz,
+                                    int device, void *stream) {
+    AVTEX_ENTER(device);
+    AVTEX_REQUIRE(L >= 2 && q_start >= 0 && q_start < L && L < (int64_t(1) << 31) && dim >= 1 && ld >= dim && ldq >= dim,
+                  "synthesis_loop: bad L=%lld q_start=%lld dim=%lld", (long long)L, (long long)q_start, (long long)dim);
+    AVTEX_REQUIRE((sn == nullptr) == (dn_table == nullptr) && (sn == nullptr || (dimA >= 1 && lds >= dimA && ldd >= dimA)),
+                  "synthesis_loop: audio table and driving table go together");
+    AVTEX_REQUIRE(n_steps >= 1 && ws_f32 != nullptr && ws_acc != nullptr && choices != nullptr && n_choices != nullptr &&
+                      mt_state != nullptr && q_scratch != nullptr && q_ids != nullptr && nz != nullptr,
+                  "synthesis_loop: workspace / output pointers must not be NULL");
+    int sms = 0, cc = 0, per_sm = 0, coop = 0;
+    if (int rc = avtex_device_info(device, &sms, &cc)) return rc;
+    AVTEX_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device));
+    AVTEX_REQUIRE(coop != 0, "synthesis_loop: device does not support cooperative launch");
+    AVTEX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, synthesis_loop_kernel, SELT, 0));
+    AVTEX_REQUIRE(per_sm >= 1, "synthesis_loop: kernel does not fit on an SM");
+    int64_t grid = (int64_t)sms;                     // one 1024-thread CTA per SM
+    const int64_t need = (L + SELT / 32 - 1) / (SELT / 32);
+    if (grid > need) grid = need;
+    SynthLoopArgs a;
+    SynthStepArgs &p = a.s;
+    p.tn = tn; p.ld = ld; p.L = L; p.dim = dim; p.qn = nullptr; p.sn = sn; p.lds = lds; p.dimA = dimA; p.dn = nullptr;
+    p.temp = temp; p.alpha = alpha; p.oma = one_minus_alpha; p.th = th; p.q = q_start;
+    p.o = ws_f32; p.a = ws_f32 + L; p.v = ws_f32 + 2 * L;
+    p.acc = ws_acc; p.mx = nullptr; p.counts = nullptr; p.choices = choices; p.n_choices = n_choices; p.vals = nullptr;
+    p.host = nullptr; p.host_cap = 0; p.seq = 0; p.parity = 0;
+    a.qn_table = qn_table; a.ldq = ldq; a.dn_table = dn_table; a.ldd = ldd; a.q_start = q_start; a.n_steps = n_steps;
+    a.mt = static_cast<Mt19937 *>(mt_state); a.q_ids = q_ids; a.nz = nz; a.q_cur = q_scratch;
+    void *args[] = {(void *)&a};
+    AVTEX_CUDA(cudaLaunchCooperativeKernel((void *)synthesis_loop_kernel, dim3((unsigned)grid), dim3(SELT), args, 0,
+                                           as_stream(stream)));
+    return 0;
+}
+
+// Host test hook: `count` draws of RandomState.randint(0, n[i]) from the state (key[624], *pos), updated in place —
+// the same code the device loop runs (tests/test_host_cpu.py checks it against numpy itself).
+extern "C" int avtex_mt19937_randint_host(uint32_t *key, int *pos, const uint32_t *n, int count, uint32_t *out) {
+    AVTEX_REQUIRE(key != nullptr && pos != nullptr && n != nullptr && out != nullptr && count >= 0 && *pos >= 0 && *pos <= 624,
+                  "mt19937_randint_host: bad arguments");
+    Mt19937 st;
+    memcpy(st.key, key, sizeof(st.key));
+    st.pos = *pos;
+    for (int i = 0; i < count; ++i) {
+        AVTEX_REQUIRE(n[i] >= 1, "mt19937_randint_host: n must be >= 1");
+        out[i] = legacy_randint(&st, n[i]);
+    }
+    memcpy(key, st.key, sizeof(st.key));
+    *pos = st.pos;
     return 0;
 }
 

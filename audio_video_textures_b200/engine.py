@@ -560,6 +560,15 @@ class SynthesisWorkspace:
         self.host = torch.zeros(2 + self.host_cap, dtype=torch.int32).pin_memory()
         self.host_np = self.host.numpy()
         self.seq = 0
+        self.mt = torch.zeros(625, dtype=torch.int32, device=device)            # numpy MT19937 key[624] + pos
+        self.q_scratch = torch.zeros(1, dtype=torch.int64, device=device)
+
+    def reset(self):
+        """Back to the freshly allocated state (the step kernel and the loop kernel keep different parities)."""
+        self.acc.zero_()
+        self.mx.zero_()
+        self.host_np[:2] = 0
+        self.seq = 0
 
 
 def synthesis_step(ws: SynthesisWorkspace, tn: torch.Tensor, qrow: torch.Tensor, q: int, temp: float, alpha: float,
@@ -590,6 +599,48 @@ def synthesis_step(ws: SynthesisWorkspace, tn: torch.Tensor, qrow: torch.Tensor,
     if n <= ws.host_cap:
         return h[2:2 + n].copy()
     return ws.sel[1:n + 1].cpu().numpy()
+
+
+def mt19937_randint_host(key: np.ndarray, pos: int, ns) -> tuple:
+    """Host copy of the device generator (test hook): draws RandomState.randint(0, n) for every n in `ns` from the
+    MT19937 state (key uint32[624], pos).  Returns (draws, new_key, new_pos)."""
+    key = np.ascontiguousarray(key, dtype=np.uint32).copy()
+    ns = np.ascontiguousarray(ns, dtype=np.uint32)
+    out = np.zeros(len(ns), dtype=np.uint32)
+    p = C.c_int(int(pos))
+    _lib.call("avtex_mt19937_randint_host", key.ctypes.data_as(C.c_void_p), C.byref(p), ns.ctypes.data_as(C.c_void_p),
+              len(ns), out.ctypes.data_as(C.c_void_p))
+    return out, key, p.value
+
+
+def synthesis_loop(ws: SynthesisWorkspace, tn: torch.Tensor, qn: torch.Tensor, q_start: int, n_steps: int, temp: float,
+                   alpha: float, threshold: float, sn: torch.Tensor | None = None, dn: torch.Tensor | None = None):
+    """The whole synthesis loop in ONE cooperative launch (avtex_synthesis_loop): numpy's global MT19937 state goes
+    to the device, every step's `np.random.choice` is drawn there by the same algorithm, and the advanced state is
+    written back with np.random.set_state — the host's random stream continues exactly where the reference's loop
+    would have left it.  Returns (q_ids int32[n_steps], nz_counts int32[n_steps]) as numpy arrays."""
+    if dn is not None and dn.shape[0] < n_steps + 1:
+        raise IndexError(f"driving table has {dn.shape[0]} rows, step {n_steps} reads row {n_steps}")   # as the reference's indexing would
+    kind, key, pos, has_gauss, cached = np.random.get_state()
+    if kind != "MT19937":
+        raise RuntimeError("numpy's global generator is not MT19937")
+    host_state = np.empty(625, dtype=np.uint32)
+    host_state[:624] = key
+    host_state[624] = pos
+    ws.reset()
+    ws.mt.copy_(torch.from_numpy(host_state.view(np.int32)))
+    out = torch.empty(2 * n_steps, dtype=torch.int32, device=tn.device)
+    _lib.call("avtex_synthesis_loop", _lib.ptr(tn), tn.stride(0), tn.shape[0], tn.shape[1], _lib.ptr(qn), qn.stride(0),
+              _lib.ptr(sn), sn.stride(0) if sn is not None else 0, sn.shape[1] if sn is not None else 0,
+              _lib.ptr(dn), dn.stride(0) if dn is not None else 0, C.c_float(_f32(temp)), C.c_float(_f32(alpha)),
+              C.c_float(np.float32(1.0 - float(alpha))), C.c_float(_f32(threshold)), int(q_start), int(n_steps),
+              _lib.ptr(ws.f32), _lib.ptr(ws.acc), C.c_void_p(ws.sel.data_ptr() + 4), _lib.ptr(ws.sel), _lib.ptr(ws.mt),
+              _lib.ptr(ws.q_scratch), _lib.ptr(out), C.c_void_p(out.data_ptr() + 4 * n_steps), _dev(tn), _stream(tn))
+    h = out.cpu().numpy()
+    st = ws.mt.cpu().numpy().view(np.uint32)
+    np.random.set_state((kind, st[:624].copy(), int(st[624]), has_gauss, cached))
+    ws.reset()
+    return h[:n_steps].copy(), h[n_steps:].copy()
 
 
 def audio_start(x: torch.Tensor, d: torch.Tensor) -> int:

@@ -258,6 +258,24 @@ AVTEX_API int avtex_synthesis_step(const float *tn, int64_t ld, int64_t L, int64
                          double *ws_acc, unsigned int *ws_max, int *ws_counts, int ws_counts_len,
                          int *choices, int *n_choices, float *vals, int *host_out, int host_cap,
                          int seq, int device, void *stream);
+/* The WHOLE synthesis loop in one cooperative launch: n_steps times { avtex_synthesis_step arithmetic for query
+ * q; idx = RandomState.randint(0, n) drawn ON THE DEVICE from numpy's own MT19937 state; q = choices[idx] }.
+ * mt_state (device, 625 x 4 bytes: key[624] then pos, as returned by np.random.get_state()) is advanced in place
+ * and must be copied back into numpy afterwards (np.random.set_state), so host and device consume ONE random
+ * stream and the chosen sequence is bit-identical to the reference's host loop.  qn_table: normalised query rows
+ * [L, dim]; dn_table: normalised driving-audio rows, row step+1 is used at step `step` (cvt/validate.py:417).
+ * ws_acc: 8 doubles, ZEROED by the caller; q_scratch: one int64.  q_ids / nz [n_steps] receive the chosen window
+ * and the survivor count of every step.  No host interaction until the kernel ends.
+ * replaces: the `while len(new_frames) < max_length` loop of cvt/validate.py:324-572 at the embedding boundary. */
+AVTEX_API int avtex_synthesis_loop(const float *tn, int64_t ld, int64_t L, int64_t dim, const float *qn_table,
+                         int64_t ldq, const float *sn, int64_t lds, int64_t dimA, const float *dn_table,
+                         int64_t ldd, float temp, float alpha, float one_minus_alpha, float th,
+                         int64_t q_start, int n_steps, float *ws_f32, double *ws_acc, int *choices,
+                         int *n_choices, void *mt_state, int64_t *q_scratch, int *q_ids, int *nz,
+                         int device, void *stream);
+/* Host test hook for the device generator: out[i] = RandomState.randint(0, n[i]) drawn from (key[624], *pos),
+ * which are advanced in place.  No GPU involved. */
+AVTEX_API int avtex_mt19937_randint_host(uint32_t *key, int *pos, const uint32_t *n, int count, uint32_t *out);
 /* out[0] = arg max_w <normalize(x[w,:]), normalize(d)> with strict '>' against a running max that
  * starts at 0 (first maximum wins; 0 if no similarity is positive).
  * replaces: the start-segment search of cvt/validate.py:222-240. */

@@ -105,3 +105,13 @@ elif what == "synth":
     w = np.array(wall[10:])
     print(f"synth C3: kernel (events) median {np.median(kern[10:]):.1f} us; host step() {np.median(w[:, 0]):.1f} us; "
           f"np.random.choice {np.median(w[:, 1]):.1f} us")
+    for n_steps in (149, 600):
+        best = 1e9
+        for rep in range(4):
+            np.random.seed(0)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            q_ids, nz = engine.synthesis_loop(st.ws, st.tn, st.qn, 10, n_steps, 0.1, 0.5, 0.3)
+            best = min(best, time.perf_counter() - t0)
+        print(f"synth C3 device loop: {n_steps} steps in {best * 1e3:.3f} ms = {best / n_steps * 1e6:.1f} us/step "
+              f"({4.0 * L * D / (best / n_steps) / 1e9 / HBM:.3f} of HBM)")

@@ -113,6 +113,32 @@ def test_fused_synthesis_step_equals_separate_kernels(eng, L, D, A, q):
         assert torch.equal(v2.cpu()[mask], vals.cpu()[mask])
 
 
+@pytest.mark.parametrize("audio", [False, True])
+def test_device_loop_equals_host_loop_and_hands_the_generator_back(eng, audio):
+    """engine.synthesis_loop (the whole loop in one persistent kernel, np.random.choice drawn on the device from
+    numpy's own MT19937 state) == one launch per step with the draw on the host: same windows, same survivor
+    counts, and numpy's global generator ends in the SAME state (the next host draw is identical)."""
+    from audio_video_textures_b200.contrastive.validate import synthesize
+    from audio_video_textures_b200.synth import synth_audio_features, synth_embeddings
+    emb = synth_embeddings(3000, 256, seed=3).cuda()
+    kw = {}
+    if audio:
+        kw = dict(alpha=0.5, q_audio=synth_audio_features(3000, 64, seed=0).cuda(),
+                  da_source=synth_audio_features(3000, 64, seed=1).cuda(),
+                  da_driving=synth_audio_features(200, 64, seed=2).cuda())
+    args = dict(temp=0.1, threshold=0.3, fps=30, new_video_length=20, window=15, stride=6)
+    np.random.seed(21)
+    host = synthesize(emb, device_loop=False, **args, **kw)
+    after_host = np.random.randint(0, 1 << 30)
+    np.random.seed(21)
+    dev = synthesize(emb, device_loop=True, **args, **kw)
+    after_dev = np.random.randint(0, 1 << 30)
+    assert dev["q_ids"] == host["q_ids"] and dev["nz_counts"] == host["nz_counts"]
+    assert dev["frame_ids"] == host["frame_ids"] and dev["jump_count"] == host["jump_count"]
+    assert after_dev == after_host
+    assert len(dev["q_ids"]) >= 98
+
+
 def test_synthesis_sequences_bit_exact(eng):
     from audio_video_textures_b200.contrastive.validate import start_segment, synthesize
     g = load_golden("contrastive_small")

@@ -294,3 +294,35 @@ def test_row_sharded_future_cost_exchange_gloo_world2(tmp_path):
     assert all(int(p["n_sweeps"]) == len(trail) for p in parts)
     np.testing.assert_allclose(parts[0]["total"], want.double().sum().item(), rtol=1e-12)
     assert int(parts[0]["nnz"]) == int((want != 0).sum()) == int(parts[1]["nnz"])
+
+
+def test_device_generator_reproduces_numpy_legacy_randint():
+    """The MT19937 + masked-rejection randint the synthesis loop kernel runs on the GPU (same source, host build)
+    against numpy itself: np.random.choice(a) == a[randint(0, len(a))], state handed over and back."""
+    from audio_video_textures_b200 import engine
+    for seed in (0, 1, 12345):
+        np.random.seed(seed)
+        np.random.rand(seed % 7)                                   # start from an arbitrary position in the stream
+        kind, key, pos, has_gauss, cached = np.random.get_state()
+        rs = np.random.RandomState(seed + 99)
+        ns = np.concatenate([rs.randint(1, 300, 700), [1, 1, 2, 3, 255, 256, 257, 65535, 65536, 2 ** 31 - 1, 4_000_000_000]])
+        want = np.array([np.random.choice(np.arange(n)) if n < 10 ** 6 else np.random.randint(0, n) for n in ns], dtype=np.uint64)
+        got, new_key, new_pos = engine.mt19937_randint_host(key, pos, ns)
+        np.testing.assert_array_equal(got.astype(np.uint64), want)
+        k2, key2, pos2 = np.random.get_state()[:3]
+        assert pos2 == new_pos and np.array_equal(key2, new_key)   # 700+ draws cross at least one 624-word refill
+        np.random.set_state((kind, new_key, new_pos, has_gauss, cached))
+        a, b = np.random.randint(0, 1000), np.random.rand()
+        np.random.set_state((kind, key2, pos2, has_gauss, cached))
+        assert a == np.random.randint(0, 1000) and b == np.random.rand()
+
+
+def test_planned_steps_matches_the_loop():
+    from audio_video_textures_b200.contrastive.validate import planned_steps
+    for max_length, W, S, ssr in ((900, 15, 6, 1), (900, 20, 4, 1), (15, 15, 6, 1), (16, 15, 6, 1), (0, 15, 6, 1), (630, 15, 6, 2)):
+        n_frames, steps = 0, 0
+        while n_frames < max_length:
+            n_frames += (W if steps == 0 else S) * ssr
+            steps += 1
+        assert planned_steps(max_length, W, S, ssr) == steps
+    assert planned_steps(900, 15, 6, 1, max_steps=7) == 7
