@@ -208,43 +208,65 @@ def gram_l2_jobs(pf: PackedFrames, jobs: list, stats: torch.Tensor | None = None
 
 
 def pairwise_l2_from_host(frames: torch.Tensor, device=None, stats: torch.Tensor | None = None, chunks: int = 8):
-    """D1 for uint8 frames that live in HOST memory: the H2D copy is cut into row chunks on a copy
-    stream and, as each chunk lands, its norms and its part of the symmetric Gram are computed on the
-    main stream (job list: the chunk's diagonal block + the rectangle against all earlier rows, stored
-    direct and transposed).  The tensor cores work underneath the PCIe transfer, so the end-to-end time is
-    the copy time plus the last chunk's tiles.  Returns (D1, PackedFrames) or None when the frames are not
-    eligible (then use pairwise_l2)."""
-    if frames.is_cuda or frames.dtype != torch.uint8:
+    """D1 for frames that live in HOST memory (uint8, or float32 as the reference's own call hands them over,
+    classic/video_textures.py:245,266): the H2D copy is cut into row chunks on a copy stream and, as each chunk
+    lands, its norms and its part of the symmetric Gram are computed on the main stream (job list: the chunk's
+    diagonal block + the rectangle against all earlier rows, stored direct and transposed).  The tensor cores
+    work underneath the PCIe transfer, so the end-to-end time is the copy time plus the last chunk's tiles.
+    float32 frames travel as they are (4 bytes per value: the copy is 4x longer) through two staging buffers and
+    are packed to centred int8 per chunk on the device; whether they were integer-valued bytes is known when the
+    last chunk has been packed (PackedFrames.exact_ok).  Returns (D1, PackedFrames) or None when the frames are
+    not eligible (then use pairwise_l2)."""
+    if frames.is_cuda or frames.dtype not in (torch.uint8, torch.float32):
         return None
     x = frames.reshape(frames.shape[0], -1)
     n, k = x.shape
-    if not x.is_contiguous() or k % 16 != 0 or n < 512:
+    is_f32 = frames.dtype == torch.float32
+    if not x.is_contiguous() or n < 512 or (k % 16 != 0 and not is_f32):
         return None
     dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
-    buf = torch.empty((n, k), dtype=torch.uint8, device=dev)
-    sqnorm = torch.empty(n, dtype=torch.int64, device=dev)
-    flags = torch.zeros(2, dtype=torch.int64, device=dev)
-    pf = PackedFrames(buf, sqnorm, k, flags, signed=False)
-    D1 = empty_matrix(n, n, dev)
+    kp = (k + 127) // 128 * 128
     step = max(256, (-(-n // chunks) + 255) // 256 * 256)
     bounds = [(c0, min(n, c0 + step)) for c0 in range(0, n, step)]
+    sqnorm = torch.empty(n, dtype=torch.int64, device=dev)
+    flags = torch.zeros(2, dtype=torch.int64, device=dev)
+    if is_f32:
+        buf = torch.empty((n, kp), dtype=torch.int8, device=dev)                 # the packed operand
+        staging = [torch.empty((step, k), dtype=torch.float32, device=dev) for _ in range(2)]
+        pf = PackedFrames(buf, sqnorm, k, flags, signed=True)
+    else:
+        buf = torch.empty((n, k), dtype=torch.uint8, device=dev)
+        pf = PackedFrames(buf, sqnorm, k, flags, signed=False)
+    D1 = empty_matrix(n, n, dev)
     main = torch.cuda.current_stream(dev)
     copy_stream = torch.cuda.Stream(dev)
     copy_stream.wait_stream(main)
-    events = []
-    with torch.cuda.stream(copy_stream):
-        for c0, c1 in bounds:
-            buf[c0:c1].copy_(x[c0:c1], non_blocking=True)
-            ev = torch.cuda.Event()
-            ev.record(copy_stream)
-            events.append(ev)
     mx = C.c_void_p(flags.data_ptr() + 8)
     d_ptr, ld = D1.data_ptr(), D1.stride(0)
-    for (c0, c1), ev in zip(bounds, events):
-        main.wait_event(ev)
-        part = buf[c0:c1]
-        _lib.call("avtex_frame_norms_u8", _lib.ptr(part), c1 - c0, k, buf.stride(0),
-                  C.c_void_p(sqnorm.data_ptr() + 8 * c0), mx, _dev(buf), _stream(buf))
+    consumed = []                                               # float path: "staging buffer i has been packed"
+    for i, (c0, c1) in enumerate(bounds):
+        with torch.cuda.stream(copy_stream):
+            if is_f32:
+                if i >= 2:
+                    copy_stream.wait_event(consumed[i - 2])
+                staging[i % 2][:c1 - c0].copy_(x[c0:c1], non_blocking=True)
+            else:
+                buf[c0:c1].copy_(x[c0:c1], non_blocking=True)
+            landed = torch.cuda.Event()
+            landed.record(copy_stream)
+        main.wait_event(landed)
+        if is_f32:
+            part = staging[i % 2][:c1 - c0]
+            _lib.call("avtex_pack_frames_f32", _lib.ptr(part), c1 - c0, k, part.stride(0),
+                      C.c_void_p(buf.data_ptr() + c0 * kp), kp, C.c_void_p(sqnorm.data_ptr() + 8 * c0),
+                      _lib.ptr(flags), mx, _dev(buf), _stream(buf))
+            ev = torch.cuda.Event()
+            ev.record(main)
+            consumed.append(ev)
+        else:
+            part = buf[c0:c1]
+            _lib.call("avtex_frame_norms_u8", _lib.ptr(part), c1 - c0, k, buf.stride(0),
+                      C.c_void_p(sqnorm.data_ptr() + 8 * c0), mx, _dev(buf), _stream(buf))
         jobs = [dict(row0=c0, rows=c1 - c0, col0=c0, cols=c1 - c0, symmetric=1, count_stats=1,
                      D=d_ptr, d_row0=0, ldd=ld, DT=d_ptr, dt_row0=0, ldt=ld)]
         if c0 > 0:
@@ -252,7 +274,10 @@ def pairwise_l2_from_host(frames: torch.Tensor, device=None, stats: torch.Tensor
                              D=d_ptr, d_row0=0, ldd=ld, DT=d_ptr, dt_row0=0, ldt=ld))
         gram_l2_jobs(pf, jobs, stats)
     buf.record_stream(copy_stream)
-    if (k + 127) // 128 * 128 * 128 * 128 < GRAM_MAX_SQNORM:
+    if is_f32:
+        for t in staging:
+            t.record_stream(copy_stream)
+    elif kp * 128 * 128 < GRAM_MAX_SQNORM:
         pf._checked = (True, "")
     return D1, pf
 

@@ -116,7 +116,31 @@ def test_streamed_host_frames_equal_resident(eng):
         np.testing.assert_allclose(P1h.cpu().numpy(), P1d.cpu().numpy(), rtol=1e-5)
     res = eng.pairwise_l2_from_host(video, chunks=3)
     assert res is not None and torch.equal(res[0], D1d)
-    assert eng.pairwise_l2_from_host(video.float()) is None and eng.pairwise_l2_from_host(video[:100]) is None
+    assert eng.pairwise_l2_from_host(video[:100]) is None
+
+
+def test_streamed_float_host_frames_equal_resident(eng):
+    """The reference's own call hands FLOAT frames to compute_D1 (classic/video_textures.py:245,266): float32 host
+    frames go through the same overlapped chunked path (staged, packed to centred int8 per chunk on the device) and
+    give the identical matrix; non-byte float features are detected after the last chunk and take the direct
+    fp32 kernel instead."""
+    from audio_video_textures_b200.classic.computeD1 import compute_D1
+    from audio_video_textures_b200.synth import synth_video
+    video = synth_video(1300, 16, 16, seed=4)
+    f = torch.tensor(4.5)
+    D1d, P1d, s1d = compute_D1(video.cuda(), f, "RGB")
+    for host in (video.float(), video.float().pin_memory()):
+        for chunks in (8, 3, 5):
+            res = eng.pairwise_l2_from_host(host, chunks=chunks)
+            assert res is not None and res[1].exact_ok and torch.equal(res[0], D1d)
+        D1h, P1h, s1h = compute_D1(host, f, "RGB")
+        assert torch.equal(D1h, D1d)
+        np.testing.assert_allclose(s1h.item(), s1d.item(), rtol=1e-6)
+    feats = torch.randn(600, 96)                                    # real-valued features: not bytes
+    res = eng.pairwise_l2_from_host(feats)
+    assert res is not None and not res[1].exact_ok
+    D, _, _ = compute_D1(feats, f, "RGB")
+    np.testing.assert_allclose(D.cpu().numpy(), torch.cdist(feats.double(), feats.double()).float().numpy(), rtol=2e-5, atol=1e-5)
 
 
 def test_gram_edge_shapes(eng):

@@ -326,3 +326,20 @@ def test_planned_steps_matches_the_loop():
             steps += 1
         assert planned_steps(max_length, W, S, ssr) == steps
     assert planned_steps(900, 15, 6, 1, max_steps=7) == 7
+
+
+def test_contrastive_parser_accepts_every_reference_flag():
+    """A full reference command line (every flag of contrastive_video_textures/main.py:41-296) parses unchanged."""
+    from audio_video_textures_b200.contrastive.main import build_parser
+    line = ("-ea slowfast -m 2 -vdata v -adata a -pdata p -fdata f -dadata d -vl a b -fps 25 -subsample 2 -temp 0.2 -th 0.3 "
+            "-l2 -nintp -size 112 -negs 10 -w 16 -train_stride 2 -stride 3 -nvl 20 -alpha 0.7 -SF 3 -long -fb --epochs 5 "
+            "--size 112 --start_epoch 2 -bs 8 -mbs 100 -lr 0.1 --lr_steps 10 --momentum 0.8 --wd 0.001 -j 2 -p 1 -lf 2 "
+            "--resume x.pth -e -da t1 t2 -daf Contrastive -daf_resume c1 c2 -ve -vf 3 --logdir l --logname n -rf r --ckpt c")
+    a = build_parser().parse_args(line.split())
+    assert (a.enc_arch, a.model_type, a.subsample_rate, a.temp, a.threshold, a.l2, a.interpolation, a.img_size) == \
+        ("slowfast", 2, 2, 0.2, 0.3, False, False, 112)
+    assert (a.driving_audio, a.da_feats, a.daf_resume, a.evaluate, a.mini_batchsize, a.alpha, a.weight_decay) == \
+        (["t1", "t2"], "Contrastive", ["c1", "c2"], True, 100, 0.7, 0.001)
+    d = build_parser().parse_args([])
+    assert (d.lr, d.epochs, d.workers, d.ckpt, d.train_stride, d.n_negs, d.long, d.frames_bar) == \
+        (10e-3, 60, 4, "./ckpt", 4, 20, False, False)
