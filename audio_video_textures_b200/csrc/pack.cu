@@ -232,3 +232,39 @@ extern "C" int avtex_frame_norms_u8_push(const uint8_t *frames, int64_t n, int64
     dst.count = num_dst;
     return launch_norms(frames, n, k, ld, row0, dst, device, stream);
 }
+
+// ---------------------------------------------------------------- (f1) window construction
+// out[w, t, :] = rows[idx[w * win + t], :]   (idx < 0: zero row — the reference zero-pads its chunks,
+// cvt/utils/utils.py:252).  One CTA per output row; 128-bit copies when the row size and both bases allow it.
+// HBM-bound gather: the frames of a window are contiguous in the clip, so consecutive CTAs read consecutive rows.
+namespace {
+__global__ void __launch_bounds__(PACK_THREADS)
+gather_rows_kernel(const uint8_t *__restrict__ rows, int64_t row_bytes, int64_t pitch, int64_t n_rows,
+                   const int *__restrict__ idx, uint8_t *__restrict__ out) {
+    const int64_t o = blockIdx.x;
+    const int src_row = idx[o];
+    uint8_t *dst = out + o * row_bytes;
+    const bool live = src_row >= 0 && src_row < n_rows;
+    const uint8_t *src = rows + (live ? int64_t(src_row) : 0) * pitch;
+    const bool vec = ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0;
+    const int64_t nv = vec ? (row_bytes & ~int64_t(15)) : 0;
+    for (int64_t c = int64_t(threadIdx.x) * 16; c < nv; c += int64_t(PACK_THREADS) * 16) {
+        const uint4 v = live ? __ldg(reinterpret_cast<const uint4 *>(src + c)) : make_uint4(0, 0, 0, 0);
+        *reinterpret_cast<uint4 *>(dst + c) = v;
+    }
+    for (int64_t c = nv + threadIdx.x; c < row_bytes; c += PACK_THREADS) dst[c] = live ? src[c] : uint8_t(0);
+}
+}  // namespace
+
+extern "C" int avtex_gather_rows(const void *rows, int64_t row_bytes, int64_t pitch_bytes, int64_t n_rows,
+                                 const int *idx, int64_t n_out, void *out, int device, void *stream) {
+    AVTEX_ENTER(device);
+    AVTEX_REQUIRE(row_bytes >= 1 && pitch_bytes >= row_bytes && n_rows >= 1 && n_out >= 1 && n_out < (int64_t(1) << 31) &&
+                      rows != nullptr && idx != nullptr && out != nullptr,
+                  "gather_rows: bad arguments row_bytes=%lld n_rows=%lld n_out=%lld", (long long)row_bytes,
+                  (long long)n_rows, (long long)n_out);
+    gather_rows_kernel<<<(unsigned)n_out, PACK_THREADS, 0, as_stream(stream)>>>(
+        static_cast<const uint8_t *>(rows), row_bytes, pitch_bytes, n_rows, idx, static_cast<uint8_t *>(out));
+    AVTEX_LAUNCH_CHECK();
+    return 0;
+}

@@ -282,6 +282,29 @@ AVTEX_API int avtex_mt19937_randint_host(uint32_t *key, int *pos, const uint32_t
 AVTEX_API int avtex_audio_start(const float *x, int64_t ld, int64_t rows, int64_t dim, const float *d,
                       float *sims_ws, int *out, int device, void *stream);
 
+/* ---------------------------------------------------------------- (f1) window construction
+ * out[o, :] = rows[idx[o], :] (row_bytes bytes each; idx[o] < 0 or >= n_rows gives a zero row): assembles the
+ * [n_windows, window, frame] tensors an encoder consumes straight from the device-resident clip, from an index
+ * plan (true windows w*S .. w*S+W, or the reference's per-step chunk layout with its zero padding).
+ * replaces: the host-side fancy indexing + chunk copies of cvt/validate.py:380-395, cvt/utils/utils.py:233-260 and
+ * the per-window slicing of cvt/models/models.py:355-362. */
+AVTEX_API int avtex_gather_rows(const void *rows, int64_t row_bytes, int64_t pitch_bytes, int64_t n_rows,
+                      const int *idx, int64_t n_out, void *out, int device, void *stream);
+
+/* ---------------------------------------------------------------- (f3) audio front end
+ * Log-mel spectrogram in the reference's float64 arithmetic: frame f = samples [f*hop, f*hop + win_len) of `wave`
+ * (device, fp64, [n_samples] or [n_samples, channels] averaged to mono) times `window`, zero padded to fft_len,
+ * |rfft|, times the mel matrix `mel` ([fft_len/2+1, n_mel] row-major, device fp64), log(. + log_offset) -> out
+ * [n_frames, n_mel] fp32.  window / mel are small host-computed tables (contrastive/audio_frontend.py).
+ * replaces: cvt/utils/mel_features.py:72-93 (stft_magnitude), :188-223 (log_mel_spectrogram). */
+AVTEX_API int avtex_logmel(const double *wave, int64_t n_samples, int channels, int win_len, int hop, int fft_len,
+                 const double *window, const double *mel, int n_mel, double log_offset, float *out,
+                 int64_t n_frames, int device, void *stream);
+/* out[e, t, :] = logmel[e*hop + t, :] for t < win: the VGGish examples.
+ * replaces: mel_features.frame on the feature rows, cvt/utils/vggish_utils.py:57-69. */
+AVTEX_API int avtex_frame_examples(const float *logmel, int64_t n_frames, int n_mel, int win, int hop, float *out,
+                         int64_t n_examples, int device, void *stream);
+
 /* Test hook: the tile visiting order of avtex_gram_l2_s8 for TM x TN tiles (128 x 256).  Returns the
  * number of tiles; fills tm_out/tn_out (capacity entries) when non-NULL.  Host only. */
 AVTEX_API int avtex_gram_tile_schedule(int TM, int TN, int symmetric, int *tm_out, int *tn_out, int capacity);

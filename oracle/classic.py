@@ -107,6 +107,40 @@ def compute_D1(frames: torch.Tensor, sigma_factor, feats: str = "RGB", audio=Non
     return D1, P1, sigma
 
 
+def feature_mode_D1(image_feats: torch.Tensor, feats: str = "ResNet", audio_feats=None, fps: int = 30,
+                    slow: bool = False, batch_size: int = 128) -> torch.Tensor:
+    """D1 of the non-RGB modes given the producers' outputs (the ResNet-18 / VGGish networks themselves are
+    feature producers): computeD1.py:105-116 (ResNet dense), :117-148 (ResNet tiled), :155-192 (ResNet_VGGish
+    dense), :194-236 (ResNet_VGGish tiled).  Reproduces the tiled loops' skipped blocks (`range(0, N - bs, bs)`,
+    `continue` on ragged blocks) and their initial values (ones / zeros), and the `.repeat(fps, 1)` tiling of the
+    per-second audio features.  The tiled ResNet branch re-normalises A on every column block (idempotent up to
+    an ulp); it is normalised once here."""
+    import torch.nn.functional as F
+    x = image_feats
+    if feats == "ResNet_VGGish":
+        n = int(len(x) / fps) * fps
+        a = audio_feats[: int(len(image_feats) / fps)].repeat(fps, 1)
+        x = torch.cat((x[:n], a), dim=1)
+    n = len(x)
+    normalise = (feats == "ResNet") or not slow
+    if not slow:
+        A = x.unsqueeze(0).repeat(n, 1, 1)
+        B = x.unsqueeze(1).repeat(1, n, 1)
+        if normalise:
+            A, B = F.normalize(A, dim=2), F.normalize(B, dim=2)
+        return torch.norm(A - B, dim=2)
+    D1 = torch.ones((n, n)) if feats == "ResNet" else torch.zeros((n, n))
+    for i in range(0, n, batch_size):
+        fa = x[i:i + batch_size].unsqueeze(0).repeat(batch_size, 1, 1)
+        for j in range(0, n - batch_size, batch_size):
+            fb = x[j:j + batch_size].unsqueeze(1).repeat(1, batch_size, 1)
+            if fa.shape != fb.shape:
+                continue
+            a_, b_ = (F.normalize(fa, dim=2), F.normalize(fb, dim=2)) if normalise else (fa, fb)
+            D1[i:i + batch_size, j:j + batch_size] = torch.norm(a_ - b_, dim=2).permute(1, 0)
+    return D1
+
+
 # --------------------------------------------------------------------------- D2
 def binomial_weights(filter_size: int) -> torch.Tensor:
     """computeD2.py:34 — coeffs((0.5x+0.5)^(fs-1)) in float64, cast to fp32."""

@@ -39,6 +39,41 @@ def target_order(q_id: int, L: int) -> np.ndarray:
     return np.concatenate((np.array([pos_id]), n_ids), axis=0)
 
 
+def frame_level_step_logits(frames: torch.Tensor, q_id: int, L: int, W: int, S: int, mbs: int, temp: float, embed):
+    """One synthesis step from FRAMES, as the reference runs it (num_gpus = 1): validate.py:329 (query window),
+    :365-388 (target frames: union of the target windows in first-seen order), utils.py:233-260
+    (split_into_overlapping_segments incl. its start = idx*S*(mbs-1)), models.py:355-362 (mbs windows per chunk),
+    :351-352,412-417 (similarity), validate.py:481-493,522 (result layout).  `embed(windows [n, W, ...]) -> [n, D]`
+    stands for the encoder stack.  Returns (target_segment_ids, logits [n_targets])."""
+    ids = target_order(q_id, L)
+    tf = []
+    for i in ids:
+        tf.extend(list(np.arange(i * S, i * S + W)))
+    tf = np.array(tf)
+    _, first = np.unique(tf, return_index=True)
+    tf = tf[np.sort(first)]
+    t_video = frames[tf]
+    num_inputs = t_video.size(0)
+    total_segments = math.ceil((num_inputs - W) / S)
+    chunk_size = mbs * S + W
+    batch_size = math.ceil(total_segments / mbs)
+    batched = torch.zeros(*([batch_size, chunk_size] + list(t_video.size()[1:])), dtype=t_video.dtype)
+    for idx in range(batch_size):
+        start = idx * S * (mbs - 1)
+        end = min(start + chunk_size, num_inputs)
+        batched[idx, :end - start] = t_video[start:end]
+    q = embed(frames[q_id * S: q_id * S + W].unsqueeze(0))
+    output = torch.zeros(len(ids), dtype=torch.float32)
+    num_valid = len(ids)
+    for itr in range(batch_size):
+        wins = torch.stack([batched[itr, i * S: i * S + W] for i in range(mbs)])
+        b_out = similarity_chunk(q, embed(wins).unsqueeze(0), temp).view(-1)
+        take = min(num_valid, mbs)
+        output[itr * mbs: itr * mbs + take] = b_out[:take]
+        num_valid -= mbs
+    return ids, output
+
+
 def similarity_chunk(q: torch.Tensor, t: torch.Tensor, temp: float) -> torch.Tensor:
     """models.py:351-352,412-417 for one replica: q [B,D], t [B,T,D] -> [B,T]."""
     q = F.normalize(q, dim=1).unsqueeze(1)

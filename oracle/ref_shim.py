@@ -68,9 +68,10 @@ class _Identity3D(torch.nn.Module):
         return x
 
 
-def load_contrastive_model(temp: float, mini_batchsize: int, model_type: int = 1):
+def load_contrastive_model(temp: float, mini_batchsize: int, model_type: int = 1, window: int = 1, stride: int = 1):
     """Builds the reference ContrastivePredictionTemporal with identity encoders
-    (window=1, stride=1, 1x1 'frames' whose channel vector is the embedding)."""
+    (default window=1, stride=1, 1x1 'frames' whose channel vector is the embedding; with window > 1 the class's
+    own AdaptiveAvgPool3d makes a window's embedding the mean of its frames' channel vectors)."""
     for name in ["librosa", "resampy", "soundfile", "ipdb", "imageio", "IPython", "IPython.display"]:
         _stub(name)
     try:
@@ -94,7 +95,7 @@ def load_contrastive_model(temp: float, mini_batchsize: int, model_type: int = 1
     sys.path.insert(0, CVT)
     from models import ContrastivePredictionTemporal
     model = ContrastivePredictionTemporal(
-        _Identity3D(), _Identity3D(), None, model_type, fc_dim=0, temp=temp, window=1, stride=1,
+        _Identity3D(), _Identity3D(), None, model_type, fc_dim=0, temp=temp, window=window, stride=stride,
         threshold=0.0, mini_batchsize=mini_batchsize, enc_arch="toy")
     model.eval()
     return model

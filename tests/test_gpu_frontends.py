@@ -1,0 +1,170 @@
+"""GPU parity tests for the rows either side of the hot path: the audio front end (f3),
+window construction + embedding cache (f1), the classic feature modes and data reader (f2)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+def test_logmel_examples_match_reference():
+    """(f3) waveform_to_examples on the GPU (csrc/audio.cu, fp64 arithmetic) against the reference's float64 numpy
+    front end (cvt/utils/vggish_utils.py:27-69, mel_features.py) on stored waveforms: fp32 outputs equal the
+    reference to rounding (rtol 2e-6; north-star tolerance 1e-4), mono and 2-channel input, and against the
+    numpy oracle on a fresh waveform."""
+    from audio_video_textures_b200.contrastive import audio_frontend as af
+    from oracle import audio as oa
+    g = load_golden("frontend_audio")
+    for name in ("mono", "stereo"):
+        wave = g[f"{name}_wave"]
+        lm = af.log_mel_spectrogram(wave, audio_sample_rate=16000, log_offset=0.01, num_mel_bins=64,
+                                    lower_edge_hertz=125, upper_edge_hertz=7500)
+        np.testing.assert_allclose(lm.cpu().numpy(), g[f"{name}_ref_logmel"], rtol=2e-6, atol=2e-6)
+        ex = af.waveform_to_examples(wave, 16000)
+        assert tuple(ex.shape) == tuple(g[f"{name}_ref_examples_shape"])
+        want = oa.frame(g[f"{name}_ref_logmel"], 100, 10)
+        np.testing.assert_allclose(ex.cpu().numpy(), want, rtol=2e-6, atol=2e-6)
+    wave = oa.synth_waveform(5.3, seed=7)
+    np.testing.assert_allclose(af.waveform_to_examples(wave, 16000).cpu().numpy(), oa.waveform_to_examples(wave, 16000),
+                               rtol=2e-6, atol=2e-6)
+    with pytest.raises(NotImplementedError):
+        af.waveform_to_examples(wave, 22050)
+
+
+def test_audio_start_search_from_waveforms():
+    """(f3 + a10) source and driving waveforms -> log-mel examples on the GPU -> start segment
+    (cvt/validate.py:218-242) == the oracle's search on the reference-arithmetic examples."""
+    from audio_video_textures_b200.contrastive import audio_frontend as af
+    from audio_video_textures_b200.contrastive.validate import start_segment
+    from oracle import audio as oa
+    from oracle import contrastive as oc
+    src = oa.synth_waveform(6.0, seed=3)
+    drv = np.roll(oa.synth_waveform(6.0, seed=3), -16000 * 2)[:32000]       # the source from t = 2 s on
+    ex_s, ex_d = af.waveform_to_examples(src, 16000), af.waveform_to_examples(drv, 16000)
+    got = start_segment(ex_s.reshape(ex_s.shape[0], -1), ex_d[0].reshape(-1))
+    want = oc.start_segment(torch.from_numpy(oa.waveform_to_examples(src, 16000).copy()).float(),
+                            torch.from_numpy(oa.waveform_to_examples(drv, 16000)[0].copy()).float())
+    assert got == want == 20
+
+
+def test_window_gather_and_embedding_cache_against_reference_step():
+    """(f1) The gather kernel assembles encoder windows from the device-resident clip; with the reference's own
+    index plan (union of target frames in first-seen order, chunk start c*S*(mbs-1), mbs windows per chunk,
+    zero padding) the logits of a whole step equal the UNMODIFIED reference's (golden: its
+    split_into_overlapping_segments + ContrastivePredictionTemporal.forward, cvt/validate.py:329,365-395,442-493;
+    cvt/utils/utils.py:233-260; cvt/models/models.py:355-417).  The cache itself encodes every TRUE window once."""
+    from audio_video_textures_b200 import engine
+    from audio_video_textures_b200.contrastive import windows as wn
+    g = load_golden("frontend_windows")
+    frames = torch.from_numpy(g["frames"]).cuda()
+    W, S, mbs, L = (int(g[k]) for k in ("W", "S", "mbs", "L"))
+    temp = float(g["temp"])
+    calls = []
+
+    def encoder(wins):                                     # identity 3D encoder + the class's AdaptiveAvgPool3d
+        calls.append(wins.shape[0])
+        return wins.mean(dim=(1, 3, 4))
+
+    cache = wn.EmbeddingCache(frames, encoder, W, S, batch=8)
+    assert cache.L == L and cache.table.shape == (L, frames.shape[1]) and sum(calls) == L     # each window encoded ONCE
+    for w in (0, 7, L - 1):
+        np.testing.assert_allclose(cache.table[w].cpu().numpy(), g["frames"][w * S: w * S + W].mean(axis=(0, 2, 3)), rtol=1e-6, atol=1e-7)
+    for q in (3, 0, L - 1, 11):
+        seg, qe, te = cache.reference_step_embeddings(q, mbs)
+        np.testing.assert_array_equal(seg, g[f"q{q}_segment_ids"])
+        _, tframes = wn.reference_target_frames(q, L, W, S)
+        np.testing.assert_array_equal(tframes, g[f"q{q}_frame_ids"])
+        tn = engine.l2_normalize_rows(te)
+        qn = engine.l2_normalize_rows(qe.view(1, -1))
+        logits = engine.cosine_scores(tn, qn[0], temp).cpu().numpy()[:len(seg)]
+        np.testing.assert_allclose(logits, g[f"q{q}_ref_logits"], rtol=1e-5, atol=2e-6)
+    # byte frames, explicit padding rows
+    clip = torch.randint(0, 255, (40, 6, 5, 3), dtype=torch.uint8, device="cuda")
+    plan = np.array([[0, 1, 2], [38, 39, -1], [-1, -1, -1], [5, 5, 7]], dtype=np.int32)
+    out = wn.gather_windows(clip, plan).cpu()
+    for i, row in enumerate(plan):
+        for t, fidx in enumerate(row):
+            want = clip[fidx].cpu() if fidx >= 0 else torch.zeros_like(clip[0]).cpu()
+            assert torch.equal(out[i, t], want)
+
+
+def test_cached_table_drives_synthesis_like_the_oracle():
+    """(f1) frames -> EmbeddingCache -> synthesize: the same windows as the oracle loop run on the cached table."""
+    from audio_video_textures_b200.contrastive import windows as wn
+    from audio_video_textures_b200.contrastive.validate import synthesize
+    from oracle import contrastive as oc
+    gen = torch.Generator().manual_seed(2)
+    T, C = 2000, 48
+    base = torch.cumsum(torch.randn(T, C, 2, 2, generator=gen), 0) / 6 + torch.randn(T, C, 2, 2, generator=gen)
+    cache = wn.EmbeddingCache(base.cuda(), lambda w: w.mean(dim=(1, 3, 4)), 15, 6, batch=128)
+    np.random.seed(4)
+    want = oc.synthesize(cache.table.cpu(), 0.1, 0.3, 150, 30, 5, 15, 6, q_start=10, return_debug=True)
+    if min(want["margins"]) < 1e-5:
+        pytest.skip("fixture too close to the threshold cut")
+    np.random.seed(4)
+    got = synthesize(cache.table, temp=0.1, threshold=0.3, fps=30, new_video_length=5, window=15, stride=6, q_start=10)
+    assert got["q_ids"] == want["q_ids"] and got["frame_ids"] == want["frame_ids"]
+
+
+def test_feature_modes_match_reference():
+    """(f2) compute_D1(feats="ResNet" / "ResNet_VGGish") against the reference's own branches
+    (classic/computeD1.py:98-238, run with seeded toy producers in place of the pretrained networks): dense and
+    tiled ("slow") forms incl. the blocks the reference's loops never visit, sigma and P1."""
+    from audio_video_textures_b200.classic import computeD1 as cd
+    g = load_golden("frontend_features")
+    frames = torch.from_numpy(g["frames"])
+    feats = torch.from_numpy(g["image_feats"]).cuda()
+    f = torch.tensor(float(g["f"]))
+    state = {"at": 0}
+
+    def image_features(batch):                             # the stored producer output, handed out batch by batch
+        b = batch.shape[0]
+        out = feats[state["at"]: state["at"] + b]
+        state["at"] += b
+        return out
+
+    cd.IMAGE_FEATURES = image_features
+    cd.AUDIO_FEATURES = lambda audio, sr: torch.from_numpy(g["audio_feats"])
+    try:
+        D1, P1, s = cd.compute_D1(frames, f, "ResNet", slow=False)
+        np.testing.assert_allclose(D1.cpu().numpy(), g["ref_D1_dense"], rtol=1e-5, atol=2e-7)
+        np.testing.assert_allclose(float(s), float(g["ref_sigma_dense"]), rtol=1e-5)
+        np.testing.assert_allclose(P1.cpu().numpy(), g["ref_P1_dense"], rtol=1e-4)
+        state["at"] = 0
+        D1s, _, ss = cd.compute_D1(frames, f, "ResNet", slow=True, batch_size=16)
+        np.testing.assert_allclose(D1s.cpu().numpy(), g["ref_D1_slow16"], rtol=1e-5, atol=2e-7)
+        assert np.array_equal(D1s.cpu().numpy() == 1.0, g["ref_D1_slow16"] == 1.0)
+        np.testing.assert_allclose(float(ss), float(g["ref_sigma_slow16"]), rtol=1e-5)
+        fps, sr = int(g["fps"]), int(g["sr"])
+        for slow, key in ((False, "joint_dense"), (True, "joint_slow16")):
+            state["at"] = 0
+            Dj, _, sj = cd.compute_D1(frames, f, "ResNet_VGGish", audio=g["audio"], sr=sr, fps=fps, slow=slow, batch_size=16)
+            np.testing.assert_allclose(Dj.cpu().numpy(), g[f"ref_D1_{key}"], rtol=1e-5, atol=1e-6)
+            np.testing.assert_allclose(float(sj), float(g[f"ref_sigma_{key}"]), rtol=1e-5)
+    finally:
+        cd.IMAGE_FEATURES = cd.AUDIO_FEATURES = None
+    with pytest.raises(NotImplementedError):
+        cd.compute_D1(frames, f, "L2")
+
+
+def test_read_data_sources_feed_the_distance_kernel(tmp_path):
+    """(f2) the reader the reference imports but does not ship (classic/video_textures.py:26,245): synthetic, .npy and
+    .pt clips arrive as uint8 [N,H,W,3] and give the same D1 as the float frames the reference would pass."""
+    import argparse
+
+    from audio_video_textures_b200.classic.computeD1 import compute_D1
+    from audio_video_textures_b200.classic.utils import read_data
+    from audio_video_textures_b200.synth import synth_video
+    video = synth_video(600, 12, 16, seed=6)
+    np.save(tmp_path / "clipA.npy", video.numpy())
+    torch.save(video, tmp_path / "clipB.pt")
+    f = torch.tensor(4.5)
+    want = compute_D1(video.float().cuda(), f, "RGB")[0]
+    for name, args in (("synthetic", argparse.Namespace(synthetic="600,12,16,6", vdata=None, fps=30, sr=22050)),
+                       ("clipA", argparse.Namespace(synthetic=None, vdata=str(tmp_path), fps=30, sr=22050)),
+                       ("clipB", argparse.Namespace(synthetic=None, vdata=str(tmp_path), fps=30, sr=22050))):
+        frames, vid, fps, audio, sr, _ = read_data(args, name)
+        assert frames.dtype == torch.uint8 and tuple(frames.shape) == (600, 12, 16, 3) and fps == 30
+        assert torch.equal(compute_D1(frames, f, "RGB")[0], want)

@@ -148,3 +148,53 @@ def test_compute_Paudio_matches_reference_module():
         finally:
             sys.path.remove(ref_dir)
     np.testing.assert_allclose(float(mine.sum()), 1.0, rtol=1e-5)
+
+
+def test_audio_frontend_oracle_matches_reference_vectors():
+    """(f3) oracle/audio.py against tests/golden/frontend_audio.npz (the unmodified reference mel_features /
+    vggish_utils run on the stored waveforms)."""
+    from oracle import audio as oa
+    g = load_golden("frontend_audio")
+    for name in ("mono", "stereo"):
+        wave = g[f"{name}_wave"]
+        ex = oa.waveform_to_examples(wave, 16000)
+        assert tuple(ex.shape) == tuple(g[f"{name}_ref_examples_shape"])
+        lm = oa.log_mel_spectrogram(wave if wave.ndim == 1 else wave.mean(axis=1))
+        np.testing.assert_allclose(lm, g[f"{name}_ref_logmel"], rtol=1e-9, atol=1e-12)
+        np.testing.assert_allclose(np.asarray(ex).sum(), float(g[f"{name}_ref_examples_sum"]), rtol=1e-9)
+
+
+def test_feature_mode_oracle_matches_reference_vectors():
+    """(f2) oracle.classic.feature_mode_D1 against the reference's compute_D1(feats="ResNet"/"ResNet_VGGish") run
+    with seeded toy producers patched in for the pretrained networks (tests/golden/frontend_features.npz)."""
+    from oracle import classic
+    g = load_golden("frontend_features")
+    img, aud = torch.from_numpy(g["image_feats"]), torch.from_numpy(g["audio_feats"])
+    fps = int(g["fps"])
+    np.testing.assert_allclose(classic.feature_mode_D1(img, "ResNet").numpy(), g["ref_D1_dense"], rtol=1e-6, atol=1e-7)
+    slow = classic.feature_mode_D1(img, "ResNet", slow=True, batch_size=16).numpy()
+    np.testing.assert_allclose(slow, g["ref_D1_slow16"], rtol=1e-5, atol=2e-7)
+    assert np.array_equal(slow == 1.0, g["ref_D1_slow16"] == 1.0)                 # the skipped blocks keep their ones
+    np.testing.assert_allclose(classic.feature_mode_D1(img, "ResNet_VGGish", aud, fps).numpy(), g["ref_D1_joint_dense"],
+                               rtol=1e-6, atol=1e-7)
+    js = classic.feature_mode_D1(img, "ResNet_VGGish", aud, fps, slow=True, batch_size=16).numpy()
+    np.testing.assert_allclose(js, g["ref_D1_joint_slow16"], rtol=1e-6, atol=1e-6)
+    P1, sigma = classic.sigma_and_probs(torch.from_numpy(g["ref_D1_dense"]), torch.tensor(float(g["f"])))
+    np.testing.assert_allclose(float(sigma), float(g["ref_sigma_dense"]), rtol=1e-6)
+    np.testing.assert_allclose(P1.numpy(), g["ref_P1_dense"], rtol=1e-5)
+
+
+def test_frame_level_step_oracle_matches_reference_vectors():
+    """(f1) oracle.contrastive.frame_level_step_logits against the reference's own validate-step at frame level
+    (its split_into_overlapping_segments + ContrastivePredictionTemporal.forward with an identity 3D encoder,
+    tests/golden/frontend_windows.npz)."""
+    from oracle import contrastive as oc
+    g = load_golden("frontend_windows")
+    frames = torch.from_numpy(g["frames"])
+    W, S, mbs, L = (int(g[k]) for k in ("W", "S", "mbs", "L"))
+    temp = float(g["temp"])
+    embed = lambda wins: wins.mean(dim=(1, 3, 4))               # identity encoder + AdaptiveAvgPool3d over (window, H, W)
+    for q in (3, 0, L - 1, 11):
+        ids, logits = oc.frame_level_step_logits(frames, q, L, W, S, mbs, temp, embed)
+        np.testing.assert_array_equal(ids, g[f"q{q}_segment_ids"])
+        np.testing.assert_allclose(logits.numpy(), g[f"q{q}_ref_logits"], rtol=1e-5, atol=2e-6)
