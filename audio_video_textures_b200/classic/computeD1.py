@@ -72,7 +72,10 @@ def _feature_distances(feats: torch.Tensor, normalise: bool, slow: bool, batch_s
     """D1 of the feature modes.  Dense (`slow=False`, computeD1.py:105-116 / 174-192): all pairs.  Tiled
     (`slow=True`, :117-148 / 194-236): the reference only visits FULL bs x bs blocks with column start
     j < N - bs and skips ragged row blocks (`continue` on a shape mismatch), leaving its initial value
-    (`fill`: ones for ResNet, zeros for ResNet_VGGish) everywhere else — reproduced, not fixed."""
+    (`fill`: ones for ResNet, zeros for ResNet_VGGish) everywhere else — reproduced, not fixed.  One thing is NOT
+    reproducible by anyone: the tiled ResNet loop re-normalises block A on every column block but B only once
+    (:135-136), so the reference's diagonal is rounding noise (exact 0 or ~1e-8) and its `nonzero` count — hence
+    sigma — moves by up to N entries of N^2 with the arithmetic library; here the diagonal is exactly 0."""
     x = engine.l2_normalize_rows(feats) if normalise else feats.contiguous()
     n = x.shape[0]
     D1 = engine.pairdist_direct(x)

@@ -316,12 +316,16 @@ def hbm_rooflines(dev, peaks):
         out.append({"kernel": kernel, "bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                     "frac": gbs / peaks["hbm_gbs"], "ms": ms, "algorithmic_bytes": nbytes, "what": what})
 
-    ms, pf = timed(lambda: engine.pack_frames(frames))
-    line("frame_norms_u8_warp_kernel", float(n) * k, ms, f"K0: {n} rows of {k} B read once")
+    x = frames.reshape(n, -1)
+    sq = torch.empty(n, dtype=torch.int64, device=dev)
+    fl = torch.zeros(2, dtype=torch.int64, device=dev)
+    ms, _ = timed(lambda: engine.frame_norms_rows(x, 0, n, sq, fl))
+    line("frame_norms_u8_kernel (12 KB rows)", float(n) * k, ms, f"K0: {n} rows of {k} B read once")
+    pf = engine.pack_frames(frames)
     D1 = engine.gram_l2(pf)
     m = engine.filtered_size(n, fs, 1)
     ms, (D2, D3) = timed(lambda: engine.diag_filter(D1, fs, 1, p=0.7))
-    line("diag_filter_s1_kernel<40> (stride 1, smem sliding window)", 4.0 * n * n + 8.0 * m * m, ms,
+    line("diag_filter_kernel<40,1,16> (stride 1; FP32-pipe bound, see DESIGN 4.2)", 4.0 * n * n + 8.0 * m * m, ms,
          f"K2 -m 1/2: read D1 {n}^2, write D2 + D3 {m}^2")
     del D2
     mv = torch.zeros((m + 31) // 32 * 32, dtype=torch.float32, device=dev)
