@@ -50,6 +50,7 @@ SIGNATURES = {
     "avtex_synthesis_step": [_p, _i64, _i64, _i64, _p, _p, _i64, _i64, _p, _f32, _i64, _f32, _f32, _f32, _p, _p, _p,
                              _p, _int, _p, _p, _p, _p, _int, _int, _int, _p],
     "avtex_gather_rows": [_p, _i64, _i64, _i64, _p, _i64, _p, _int, _p],
+    "avtex_assemble_frames": [_p, _i64, _int, _int, _p, _p, _p, _int, _i64, _p, _int, _p],
     "avtex_logmel": [_p, _i64, _int, _int, _int, _int, _p, _p, _int, C.c_double, _p, _i64, _int, _p],
     "avtex_frame_examples": [_p, _i64, _int, _int, _int, _p, _i64, _int, _p],
     "avtex_gram_tile_schedule": [_int, _int, _int, C.POINTER(_int), C.POINTER(_int), _int],

@@ -48,11 +48,49 @@ def read_data(args, video_name: str):
     return video, video, args.fps, None, args.sr, None
 
 
-def write_frames(frames, frame_ids, folder: str):
+def marker_columns(frame_ids, width: int, n_source: int, half: int = 4, floor_div: bool = True):
+    """Column range of the red position marker for every output frame, with the reference's slice semantics:
+    classic (video_textures.py:217-218): frame_n = int(idx * W // N), columns [frame_n-4, frame_n+4);
+    contrastive (validate.py:629-630): frame_n = int(idx * W / N), half-width 3.  A negative slice start wraps
+    around in numpy and yields an EMPTY slice there (no marker for the first frames) — reproduced."""
+    lo, hi = [], []
+    for idx in frame_ids:
+        fn = int(idx * width // n_source) if floor_div else int(idx * width / n_source)
+        a, b = fn - half, fn + half
+        if a < 0:
+            a += width                                              # numpy: negative start counts from the end
+        b = min(b, width)
+        lo.append(a)
+        hi.append(b if b > a else a)
+    return np.asarray(lo, dtype=np.int32), np.asarray(hi, dtype=np.int32)
+
+
+def assemble_frames(video, frame_ids, bar: bool = True, half: int = 4, floor_div: bool = True) -> torch.Tensor:
+    """(f4) The output clip [n_out, H, W, 3] uint8 for the chosen frame ids, gathered (and the progress bar painted)
+    on the device in one launch instead of one host copy + PIL image per frame (video_textures.py:215-226,
+    validate.py:622-634).  `video`: uint8 [N, H, W, 3], CPU or CUDA."""
+    import ctypes as C
+
+    from .. import _lib, engine
+    v = video if video.is_cuda else video.cuda()
+    v = v.contiguous()
+    n, h, w, _ = v.shape
+    ids = torch.as_tensor(np.asarray(frame_ids, dtype=np.int32)).to(v.device)
+    lo, hi = marker_columns(frame_ids, w, n, half, floor_div)
+    d_lo, d_hi = torch.from_numpy(lo).to(v.device), torch.from_numpy(hi).to(v.device)
+    out = torch.empty((len(ids), h, w, 3), dtype=torch.uint8, device=v.device)
+    _lib.call("avtex_assemble_frames", _lib.ptr(v), n, h, w, _lib.ptr(ids), _lib.ptr(d_lo), _lib.ptr(d_hi), 1 if bar else 0,
+              len(ids), _lib.ptr(out), engine._dev(v), engine._stream(v))
+    return out
+
+
+def write_frames(frames, frame_ids, folder: str, bar: bool = True):
+    """PNG files 0001.png ... of the chosen frames (video_textures.py:212-226), assembled on the GPU, one D2H copy."""
     from PIL import Image
     os.makedirs(folder, exist_ok=True)
-    for count, idx in enumerate(frame_ids):
-        Image.fromarray(np.asarray(frames[idx])).save(os.path.join(folder, "{:04d}.png".format(count + 1)))
+    clip = assemble_frames(frames, frame_ids, bar=bar).cpu().numpy()
+    for count in range(len(frame_ids)):
+        Image.fromarray(clip[count]).save(os.path.join(folder, "{:04d}.png".format(count + 1)))
 
 
 def save_video(*a, **k):

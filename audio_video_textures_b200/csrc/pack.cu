@@ -268,3 +268,49 @@ extern "C" int avtex_gather_rows(const void *rows, int64_t row_bytes, int64_t pi
     AVTEX_LAUNCH_CHECK();
     return 0;
 }
+
+// ---------------------------------------------------------------- (f4) output frame assembly
+// out[o] = video[ids[o]] with the reference's progress bar painted over rows [H-25, H-10): black, and red
+// (255, 0, 0) in columns [mark_lo[o], mark_hi[o]) (empty range = no marker).  One CTA per output frame; the bar
+// rows are written after the copy by the same CTA.  replaces: the per-frame host loop of
+// classic/video_textures.py:215-226 and cvt/validate.py:622-634 (np.array(frames[idx]) + PIL per frame).
+namespace {
+__global__ void __launch_bounds__(PACK_THREADS)
+assemble_frames_kernel(const uint8_t *__restrict__ video, int64_t n_frames, int h, int w, const int *__restrict__ ids,
+                       const int *__restrict__ mark_lo, const int *__restrict__ mark_hi, int draw_bar,
+                       uint8_t *__restrict__ out) {
+    const int64_t o = blockIdx.x;
+    const int64_t frame_bytes = int64_t(h) * w * 3;
+    const int id = ids[o];
+    const uint8_t *src = video + int64_t(id >= 0 && id < n_frames ? id : 0) * frame_bytes;
+    uint8_t *dst = out + o * frame_bytes;
+    const bool vec = ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0;
+    const int64_t nv = vec ? (frame_bytes & ~int64_t(15)) : 0;
+    for (int64_t c = int64_t(threadIdx.x) * 16; c < nv; c += int64_t(PACK_THREADS) * 16)
+        *reinterpret_cast<uint4 *>(dst + c) = __ldg(reinterpret_cast<const uint4 *>(src + c));
+    for (int64_t c = nv + threadIdx.x; c < frame_bytes; c += PACK_THREADS) dst[c] = src[c];
+    if (!draw_bar || h < 25) return;
+    __syncthreads();
+    const int lo = mark_lo[o], hi = mark_hi[o];
+    for (int i = threadIdx.x; i < 15 * w; i += PACK_THREADS) {
+        const int r = h - 25 + i / w, c = i % w;
+        uint8_t *px = dst + (int64_t(r) * w + c) * 3;
+        px[0] = (c >= lo && c < hi) ? 255 : 0;
+        px[1] = 0;
+        px[2] = 0;
+    }
+}
+}  // namespace
+
+extern "C" int avtex_assemble_frames(const uint8_t *video, int64_t n_frames, int h, int w, const int *ids,
+                                     const int *mark_lo, const int *mark_hi, int draw_bar, int64_t n_out,
+                                     uint8_t *out, int device, void *stream) {
+    AVTEX_ENTER(device);
+    AVTEX_REQUIRE(n_frames >= 1 && h >= 1 && w >= 1 && n_out >= 1 && n_out < (int64_t(1) << 31) && video != nullptr &&
+                      ids != nullptr && out != nullptr && (!draw_bar || (mark_lo != nullptr && mark_hi != nullptr)),
+                  "assemble_frames: bad arguments");
+    assemble_frames_kernel<<<(unsigned)n_out, PACK_THREADS, 0, as_stream(stream)>>>(video, n_frames, h, w, ids, mark_lo,
+                                                                                   mark_hi, draw_bar, out);
+    AVTEX_LAUNCH_CHECK();
+    return 0;
+}

@@ -291,6 +291,15 @@ AVTEX_API int avtex_audio_start(const float *x, int64_t ld, int64_t rows, int64_
 AVTEX_API int avtex_gather_rows(const void *rows, int64_t row_bytes, int64_t pitch_bytes, int64_t n_rows,
                       const int *idx, int64_t n_out, void *out, int device, void *stream);
 
+/* ---------------------------------------------------------------- (f4) output frame assembly
+ * out[o] = video[ids[o]] (uint8 [h, w, 3] frames); with draw_bar the reference's progress bar is painted over rows
+ * [h-25, h-10): black, red (255,0,0) in columns [mark_lo[o], mark_hi[o]) (host-computed with the reference's own
+ * slice semantics; an empty range draws no marker).
+ * replaces: classic/video_textures.py:215-226, cvt/validate.py:622-634 (one host copy + PIL image per frame). */
+AVTEX_API int avtex_assemble_frames(const uint8_t *video, int64_t n_frames, int h, int w, const int *ids,
+                          const int *mark_lo, const int *mark_hi, int draw_bar, int64_t n_out, uint8_t *out,
+                          int device, void *stream);
+
 /* ---------------------------------------------------------------- (f3) audio front end
  * Log-mel spectrogram in the reference's float64 arithmetic: frame f = samples [f*hop, f*hop + win_len) of `wave`
  * (device, fp64, [n_samples] or [n_samples, channels] averaged to mono) times `window`, zero padded to fft_len,

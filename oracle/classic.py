@@ -296,3 +296,19 @@ def walk(P, model_type: int, fps: int, new_video_length: int, stride: int, filte
                                       this_frame * stride + filter_size)))
         this_frame = next_frame  # noqa: F841  (reference: outside the while)
     return [int(v) for v in out], jump_count
+
+
+# --------------------------------------------------------------------------- frame assembly
+def assemble_frames(frames, new_frames_list, half: int = 4, floor_div: bool = True):
+    """video_textures.py:215-221 (classic: half-width 4, `//`) / validate.py:622-631 (contrastive: half-width 3,
+    `/`): the chosen frames with the black progress bar and the red position marker painted in."""
+    frames = np.asarray(frames)
+    out = []
+    for frame_idx in new_frames_list:
+        frames_bar = np.zeros((15, frames.shape[-2], 3))
+        frame_n = int(frame_idx * frames.shape[-2] // len(frames)) if floor_div else int(frame_idx * frames.shape[-2] / len(frames))
+        frames_bar[:, frame_n - half: frame_n + half, :] = [255, 0, 0]
+        frame_arr = np.array(frames[frame_idx])
+        frame_arr[-25:-10, :, :] = frames_bar
+        out.append(frame_arr)
+    return np.stack(out)

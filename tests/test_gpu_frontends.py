@@ -168,3 +168,22 @@ def test_read_data_sources_feed_the_distance_kernel(tmp_path):
         frames, vid, fps, audio, sr, _ = read_data(args, name)
         assert frames.dtype == torch.uint8 and tuple(frames.shape) == (600, 12, 16, 3) and fps == 30
         assert torch.equal(compute_D1(frames, f, "RGB")[0], want)
+
+
+def test_frame_assembly_matches_reference_loop(tmp_path):
+    """(f4) avtex_assemble_frames (gather + progress bar on the device) against the reference's per-frame host loop
+    (classic/video_textures.py:215-221; contrastive variant validate.py:622-631), bit for bit, including the first
+    frames whose negative slice start leaves the marker out; PNGs are written from the assembled clip."""
+    from audio_video_textures_b200.classic.utils import assemble_frames, write_frames
+    from audio_video_textures_b200.synth import synth_video
+    from oracle import classic as oc
+    video = synth_video(300, 48, 64, seed=1)
+    ids = [100, 101, 5, 0, 1, 299, 17, 18, 250, 3]
+    got = assemble_frames(video, ids).cpu().numpy()
+    np.testing.assert_array_equal(got, oc.assemble_frames(video.numpy(), ids))
+    got3 = assemble_frames(video.cuda(), ids, half=3, floor_div=False).cpu().numpy()
+    np.testing.assert_array_equal(got3, oc.assemble_frames(video.numpy(), ids, half=3, floor_div=False))
+    np.testing.assert_array_equal(assemble_frames(video, ids, bar=False).cpu().numpy(), video.numpy()[ids])
+    write_frames(video, ids[:3], str(tmp_path / "out"))
+    from PIL import Image
+    np.testing.assert_array_equal(np.asarray(Image.open(tmp_path / "out" / "0002.png")), got[1])
