@@ -136,7 +136,14 @@ def test_feature_modes_match_reference():
         D1s, _, ss = cd.compute_D1(frames, f, "ResNet", slow=True, batch_size=16)
         np.testing.assert_allclose(D1s.cpu().numpy(), g["ref_D1_slow16"], rtol=1e-5, atol=2e-7)
         assert np.array_equal(D1s.cpu().numpy() == 1.0, g["ref_D1_slow16"] == 1.0)
-        np.testing.assert_allclose(float(ss), float(g["ref_sigma_slow16"]), rtol=1e-5)
+        # sigma = f * sum / nnz: in the tiled branch the reference re-normalises A on every column block but B once, so
+        # its diagonal holds rounding noise (0 or ~1e-7) and its non-zero COUNT is reproducible only to +-N entries;
+        # with the reference's diagonal pattern the value agrees to 1e-5
+        n = D1s.shape[0]
+        np.testing.assert_allclose(float(ss), float(g["ref_sigma_slow16"]), rtol=1.5 * n / float((D1s != 0).sum()))
+        ref = g["ref_D1_slow16"]
+        ours_with_ref_count = float(g["f"]) * float(D1s.double().sum()) / float((ref != 0).sum())
+        np.testing.assert_allclose(ours_with_ref_count, float(g["ref_sigma_slow16"]), rtol=1e-5)
         fps, sr = int(g["fps"]), int(g["sr"])
         for slow, key in ((False, "joint_dense"), (True, "joint_slow16")):
             state["at"] = 0
