@@ -27,6 +27,11 @@ constexpr int FT = 128;      // threads per CTA = diagonals per CTA
 
 struct Taps64 { float w[64]; };
 struct TapsBig { float w[960]; };
+// Packed-FMA operand pairs (w[q], w[q-1]), q = 0..FS (zero outside [0, FS)), built on the host and passed as
+// 8-byte-aligned kernel parameters: FFMA2 then reads each pair straight from a uniform-register pair filled by one
+// LDCU.  Building the pairs in the kernel from the scalar taps made ptxas assemble every odd pair with two UMOVs
+// (366 UMOV + 293 LDCU for 328 FFMA2 per thread: more feeding instructions than FMAs).
+struct TapPairs { float2 wp[66]; };
 
 // Out-of-line so the 8/16 calls per thread do not multiply the (already fully unrolled) code size:
 // the first version stalled on instruction fetch (ncu: stalled_no_instruction was the top reason).
@@ -35,7 +40,7 @@ __device__ __noinline__ float pow_pos_call(float x, float p) { return pow_pos(x,
 template <int FS, int S, int FR, bool PACKED>
 __global__ void __launch_bounds__(FT)
 diag_filter_kernel(const float *__restrict__ D1, int64_t ld1, int64_t in_row0, int64_t in_rows, const Taps64 taps,
-                   int64_t a0, int64_t rows_out, int64_t m, float *__restrict__ D2, int64_t ld2,
+                   const TapPairs pairs, int64_t a0, int64_t rows_out, int64_t m, float *__restrict__ D2, int64_t ld2,
                    float *__restrict__ D3, int64_t ld3, float p, double *sum, unsigned long long *nnz) {
     __shared__ double sred[32];
     __shared__ unsigned long long nred[32];
@@ -60,10 +65,6 @@ diag_filter_kernel(const float *__restrict__ D1, int64_t ld1, int64_t in_row0, i
         // need taps q = t - 2p and q - 1, so the pair (w[q], w[q-1]) is kept as one 64-bit register value
         // (zero outside [0, FS)).  Same operation order per output as the scalar path -> identical bits,
         // half the FMA issue slots (this kernel is issue-bound at stride 1: 40 FMAs + pow per output).
-        float2 wp[FS + 1];
-#pragma unroll
-        for (int q = 0; q <= FS; ++q)
-            wp[q] = make_float2(q < FS ? taps.w[q] : 0.f, q >= 1 ? taps.w[q - 1] : 0.f);
         float2 acc2[FR / 2];
 #pragma unroll
         for (int p2 = 0; p2 < FR / 2; ++p2) acc2[p2] = make_float2(0.f, 0.f);
@@ -75,7 +76,7 @@ diag_filter_kernel(const float *__restrict__ D1, int64_t ld1, int64_t in_row0, i
 #pragma unroll
             for (int p2 = 0; p2 < FR / 2; ++p2) {
                 const int q = t - 2 * p2;
-                if (q >= 0 && q <= FS) acc2[p2] = __ffma2_rn(wp[q], x2, acc2[p2]);
+                if (q >= 0 && q <= FS) acc2[p2] = __ffma2_rn(pairs.wp[q], x2, acc2[p2]);
             }
         }
 #pragma unroll
@@ -104,22 +105,48 @@ diag_filter_kernel(const float *__restrict__ D1, int64_t ld1, int64_t in_row0, i
             }
         }
     }
-    double s = 0.0;
+    float s = 0.f;                                                          // fp32 partial over this thread's FR outputs
     int z = 0;
     float *o2 = D2 + (a_base - a0) * ld2 + b0;
     float *o3 = (D3 != nullptr) ? D3 + (a_base - a0) * ld3 + b0 : nullptr;
+    // CTA-uniform: every output of every thread is inside the matrix -> no per-output range checks, pow inlined
+    // (the hot path then is ~16 KB of straight-line code; border CTAs keep the out-of-line pow)
+    const bool all_out = interior && (a_base + FR <= a0 + rows_out) && (b_blk >= 0) && (b_blk + FT + FR - 2 < m);
+    if (all_out) {
+        const int64_t st2 = ld2 + 1, st3 = ld3 + 1;
+        if (o3 != nullptr) {
 #pragma unroll
-    for (int i = 0; i < FR; ++i) {
-        const int64_t a = a_base + i, b = b0 + i;
-        if (a < a0 + rows_out && b >= 0 && b < m) {
-            o2[i * (ld2 + 1)] = acc[i];
-            if (o3 != nullptr) o3[i * (ld3 + 1)] = pow_pos_call(acc[i], p);
-            s += (double)acc[i];
-            z += (acc[i] != 0.f);
+            for (int i = 0; i < FR; ++i) {
+                *o2 = acc[i];
+                *o3 = pow_pos(acc[i], p);
+                o2 += st2;
+                o3 += st3;
+                s += acc[i];
+                z += (acc[i] != 0.f);
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < FR; ++i) {
+                *o2 = acc[i];
+                o2 += st2;
+                s += acc[i];
+                z += (acc[i] != 0.f);
+            }
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < FR; ++i) {
+            const int64_t a = a_base + i, b = b0 + i;
+            if (a < a0 + rows_out && b >= 0 && b < m) {
+                o2[i * (ld2 + 1)] = acc[i];
+                if (o3 != nullptr) o3[i * (ld3 + 1)] = pow_pos_call(acc[i], p);
+                s += acc[i];
+                z += (acc[i] != 0.f);
+            }
         }
     }
     if (sum != nullptr) {
-        const double sd = block_reduce(s, 0.0, OpAdd<double>(), sred);
+        const double sd = block_reduce((double)s, 0.0, OpAdd<double>(), sred);
         const unsigned long long zd = block_reduce((unsigned long long)z, 0ull, OpAdd<unsigned long long>(), nred);
         if (threadIdx.x == 0) { atomicAdd(sum, sd); atomicAdd(nnz, zd); }
     }
@@ -156,20 +183,21 @@ diag_filter_generic_kernel(const float *__restrict__ D1, int64_t ld1, int64_t in
 // outputs per thread along its diagonal: (FR-1)*S+FS loads serve FR outputs
 template <int S> constexpr int filter_r() { return S == 1 ? 16 : 8; }
 
-template <int FS, int S>
+template <int FS, int S, int FR = filter_r<S>()>
 void launch_fast(const float *D1, int64_t ld1, int64_t in_row0, int64_t in_rows, const float *h_w, int64_t a0,
                  int64_t rows_out, int64_t m, float *D2, int64_t ld2, float *D3, int64_t ld3, float p,
                  double *sum, unsigned long long *nnz, cudaStream_t st) {
     Taps64 taps;
     for (int i = 0; i < 64; ++i) taps.w[i] = (i < FS) ? h_w[i] : 0.f;
-    constexpr int FR = filter_r<S>();
+    TapPairs pairs;
+    for (int q = 0; q < 66; ++q) pairs.wp[q] = make_float2(q < FS ? h_w[q] : 0.f, (q >= 1 && q <= FS) ? h_w[q - 1] : 0.f);
     dim3 grid((unsigned)((m + FR - 1 + FT - 1) / FT), (unsigned)((rows_out + FR - 1) / FR));
     static const bool packed_off = []() { const char *e = getenv("AVTEX_FILTER_FFMA2"); return e != nullptr && e[0] == '0'; }();
     if (S == 1 && !packed_off)
-        diag_filter_kernel<FS, S, FR, S == 1><<<grid, FT, 0, st>>>(D1, ld1, in_row0, in_rows, taps, a0, rows_out, m, D2, ld2, D3,
+        diag_filter_kernel<FS, S, FR, S == 1><<<grid, FT, 0, st>>>(D1, ld1, in_row0, in_rows, taps, pairs, a0, rows_out, m, D2, ld2, D3,
                                                            ld3, p, sum, nnz);
     else
-    diag_filter_kernel<FS, S, FR, false><<<grid, FT, 0, st>>>(D1, ld1, in_row0, in_rows, taps, a0, rows_out, m, D2, ld2, D3,
+    diag_filter_kernel<FS, S, FR, false><<<grid, FT, 0, st>>>(D1, ld1, in_row0, in_rows, taps, pairs, a0, rows_out, m, D2, ld2, D3,
                                                    ld3, p, sum, nnz);
 }
 
@@ -223,9 +251,13 @@ extern "C" int avtex_diag_filter_pow(const float *D1, int64_t ld1, int64_t in_ro
     AVTEX_REQUIRE(D3 == nullptr || ld3 >= m, "diag_filter: ld3 too small");
     cudaStream_t st = as_stream(stream);
     const int key = fs * 100 + stride;
+    static const int r_exp = []() { const char *e = getenv("AVTEX_FILTER_R"); return e ? atoi(e) : 0; }();
 #define AVTEX_FAST(FS_, S_)                                                                            \
     case FS_ * 100 + S_:                                                                               \
         AVTEX_REQUIRE((rows_out + filter_r<S_>() - 1) / filter_r<S_>() <= 65535, "diag_filter: too many row bands"); \
+        if (S_ == 1 && FS_ == 40 && r_exp == 32)                                                       \
+            launch_fast<FS_, S_, (S_ == 1 && FS_ == 40) ? 32 : filter_r<S_>()>(D1, ld1, in_row0, in_rows, h_w, a0, rows_out, m, D2, ld2, D3, ld3, p, sum, nnz, st); \
+        else                                                                                           \
         launch_fast<FS_, S_>(D1, ld1, in_row0, in_rows, h_w, a0, rows_out, m, D2, ld2, D3, ld3, p, sum, nnz, st); \
         break;
     switch (key) {

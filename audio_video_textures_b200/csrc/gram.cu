@@ -80,6 +80,7 @@ struct GramArgs {
     uint32_t idesc;                     // kind::i8 instruction descriptor (signed or unsigned operands)
     int num_jobs, num_tiles;
     int group_m;                        // schedule group (row-tiles) of the 2-CTA kernel
+    int l2_hint;                        // TMA L2 policy of the operand loads: 0 none, 1 A evict_last, 2 A and B evict_last
     unsigned long long *clock_probe;    // nullable: [0] SM cycles, [1] ns spent by CTA 0's first epilogue warp
     GramJob jobs[MAX_JOBS];
 };
@@ -183,7 +184,15 @@ struct EpiStats {
 // `release()` is called by lane 0 once the warp's last TMEM read has completed, so the MMA warp can
 // reuse the accumulator while the stores drain.
 
-template <typename Release>
+// Output stores.  ST = 0: plain; 1: st.global.cs (streaming, evict-first): D1 is written once and not read by this
+// kernel, so its lines should not displace the operand tiles that every wave re-reads from L2.
+template <int ST>
+__device__ __forceinline__ void st_out(float *p, float v) {
+    if (ST == 0) *p = v;
+    else asm volatile("st.global.cs.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
+}
+
+template <int ST = 0, typename Release>
 __device__ __forceinline__ void epilogue_tile(const GramArgs &args, const GramJob &job, uint32_t t_base, int64_t r0,
                                               int64_t c0, int lane, float *tile, Release release, EpiStats &st,
                                               int cc_begin = 0, int cc_end = BN / 32) {
@@ -226,7 +235,7 @@ __device__ __forceinline__ void epilogue_tile(const GramArgs &args, const GramJo
                 const float d = __fsqrt_rn(__uint2float_rn(nr + nc - 2u * g[j]));      // d^2 exact mod 2^32
                 tile[lane * EPI_PITCH + j] = d;
                 if (dt != nullptr) {
-                    *dt = d;                                      // transposed store: one 128 B line per warp
+                    st_out<ST>(dt, d);                            // transposed store: one 128 B line per warp
                     dt += job.ldt;
                 }
                 if (w_trans) { cs += d; cz += (d != 0.f); }
@@ -237,7 +246,7 @@ __device__ __forceinline__ void epilogue_tile(const GramArgs &args, const GramJo
 #pragma unroll
                 for (int i = 0; i < 32; ++i) {
                     const float d = tile[i * EPI_PITCH + lane];
-                    *dst = d;                                     // direct store: one 128 B line per warp
+                    st_out<ST>(dst, d);                           // direct store: one 128 B line per warp
                     dst += job.ldd;
                     cs += d;
                     cz += (d != 0.f);
@@ -251,7 +260,7 @@ __device__ __forceinline__ void epilogue_tile(const GramArgs &args, const GramJo
                 tile[lane * EPI_PITCH + j] = d;
                 const int64_t c = cbase + j;
                 if (dt != nullptr && r_ok && c < col_end && (!sym || r < c)) {
-                    dt[j * job.ldt] = d;
+                    st_out<ST>(dt + j * job.ldt, d);
                     if (w_trans) { cs += d; cz += (d != 0.f); }
                 }
             }
@@ -264,7 +273,7 @@ __device__ __forceinline__ void epilogue_tile(const GramArgs &args, const GramJo
                 for (int i = 0; i < 32; ++i) {
                     if (i < rows_here && c_ok && (!sym || r0 + i <= c)) {
                         const float d = tile[i * EPI_PITCH + lane];
-                        dst[i * job.ldd] = d;
+                        st_out<ST>(dst + i * job.ldd, d);
                         if (!sym || r0 + i < c || job.DT == nullptr) { cs += d; cz += (d != 0.f); }
                     }
                 }
@@ -496,6 +505,13 @@ __device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const CUtensorMap 
         "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
         ::"r"(dst), "l"(map), "r"(bar & 0xFEFFFFFFu), "r"(c0), "r"(c1) : "memory");
 }
+__device__ __forceinline__ void tma_load_2d_2sm_hint(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1,
+                                                     uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint "
+        "[%0], [%1, {%3, %4}], [%2], %5;"
+        ::"r"(dst), "l"(map), "r"(bar & 0xFEFFFFFFu), "r"(c0), "r"(c1), "l"(policy) : "memory");
+}
 __device__ __forceinline__ void tmem_alloc_2cta(uint32_t dst_smem, uint32_t cols) {
     asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
@@ -562,6 +578,36 @@ __host__ __device__ inline void decode_tile2(int t, int TM, int TN, int symmetri
     }
 }
 
+// The same decode for a caller whose tile indices only grow (every role of the kernel walks t, t + stride, ...):
+// the cursor remembers the group reached so far, so the search over groups is amortised O(1) per tile.  Scanning
+// from group 0 for every tile (decode_tile2) costs ~25 x 16 loop iterations at N = 100000 — about 3 us of
+// dependent integer work in the single TMA-producer thread at every tile boundary, longer than the 2.2 us of
+// operand stages the ring buffers ahead.
+struct TileCursor {
+    int job = -1, g = 0, base = 0;
+};
+__device__ __forceinline__ void decode_tile2_cursor(TileCursor &cur, int job_id, int t, int TM, int TN, int symmetric,
+                                                    int *tm, int *tn, int GROUP_M2) {
+    if (!symmetric) { decode_tile2(t, TM, TN, 0, tm, tn, GROUP_M2); return; }
+    if (cur.job != job_id) { cur.job = job_id; cur.g = 0; cur.base = 0; }
+    int gm, cnt = sym2_group_count(cur.g, TM, TN, &gm, GROUP_M2);
+    while (t - cur.base >= cnt) {
+        cur.base += cnt;
+        ++cur.g;
+        cnt = sym2_group_count(cur.g, TM, TN, &gm, GROUP_M2);
+    }
+    int r = t - cur.base;
+    const int first = cur.g * GROUP_M2;
+    for (int j = 0; j < GROUP_M2; ++j) {
+        if (first + j >= TN) break;
+        const int c = (gm < j + 1) ? gm : (j + 1);
+        if (r < c) { *tm = first + r; *tn = first + j; return; }
+        r -= c;
+    }
+    *tm = first + r % gm;
+    *tn = first + GROUP_M2 + r / gm;
+}
+
 int count_tiles2(int TM, int TN, int symmetric, int GROUP_M2 = GROUP_M2_DEFAULT) {
     if (!symmetric) return TM * TN;
     int total = 0, gm;
@@ -569,6 +615,7 @@ int count_tiles2(int TM, int TN, int symmetric, int GROUP_M2 = GROUP_M2_DEFAULT)
     return total;
 }
 
+template <int ST>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS2, 1)
 gram_l2_s8_2cta_kernel(const __grid_constant__ CUtensorMap map, const GramArgs args) {
     extern __shared__ uint8_t smem_raw[];
@@ -603,10 +650,14 @@ gram_l2_s8_2cta_kernel(const __grid_constant__ CUtensorMap map, const GramArgs a
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
+            uint64_t pol_last = 0;
+            if (args.l2_hint) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_last));
+            TileCursor cur;
             for (int t = cluster_id; t < args.num_tiles; t += num_clusters) {
                 int tm, tn, lt;
-                const GramJob &job = args.jobs[find_job(args, t, &lt)];
-                decode_tile2(lt, job.TM, job.TN, job.symmetric, &tm, &tn, args.group_m);
+                const int jid = find_job(args, t, &lt);
+                const GramJob &job = args.jobs[jid];
+                decode_tile2_cursor(cur, jid, lt, job.TM, job.TN, job.symmetric, &tm, &tn, args.group_m);
                 int row_a = int(job.row0) + tm * BM2 + int(rank) * BM;
                 int row_b = int(job.col0) + tn * BN + int(rank) * (BN / 2);
                 if (row_a >= args.n) row_a = 0;           // fully out-of-range half: load anything, stores are masked
@@ -616,8 +667,10 @@ gram_l2_s8_2cta_kernel(const __grid_constant__ CUtensorMap map, const GramArgs a
                     const uint32_t sa = tiles + stage * STAGE2_BYTES, sb = sa + A_BYTES;
                     if (leader) mbar_arrive_expect_tx(full_bar + 8 * stage, 2 * STAGE2_BYTES);
                     else mbar_arrive_cluster(full_bar + 8 * stage, 0);
-                    tma_load_2d_2sm(sa, &map, full_bar + 8 * stage, kb * BKB, row_a);
-                    tma_load_2d_2sm(sb, &map, full_bar + 8 * stage, kb * BKB, row_b);
+                    if (args.l2_hint >= 1) tma_load_2d_2sm_hint(sa, &map, full_bar + 8 * stage, kb * BKB, row_a, pol_last);
+                    else tma_load_2d_2sm(sa, &map, full_bar + 8 * stage, kb * BKB, row_a);
+                    if (args.l2_hint >= 2) tma_load_2d_2sm_hint(sb, &map, full_bar + 8 * stage, kb * BKB, row_b, pol_last);
+                    else tma_load_2d_2sm(sb, &map, full_bar + 8 * stage, kb * BKB, row_b);
                     if (++stage == STAGES2) { stage = 0; phase ^= 1; }
                 }
             }
@@ -662,15 +715,17 @@ gram_l2_s8_2cta_kernel(const __grid_constant__ CUtensorMap map, const GramArgs a
         long long c0 = 0;
         unsigned long long g0 = 0;
         if (probe) { c0 = clock64(); asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g0)); }
+        TileCursor cur;
         for (int t = cluster_id; t < args.num_tiles; t += num_clusters) {
             int tm, tn, lt;
-            const GramJob &job = args.jobs[find_job(args, t, &lt)];
-            decode_tile2(lt, job.TM, job.TN, job.symmetric, &tm, &tn, args.group_m);
+            const int jid = find_job(args, t, &lt);
+            const GramJob &job = args.jobs[jid];
+            decode_tile2_cursor(cur, jid, lt, job.TM, job.TN, job.symmetric, &tm, &tn, args.group_m);
             mbar_wait(tfull_bar + 8 * acc, acc_phase);
             tc_fence_after();
             const uint32_t t_base = tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(acc * BN);
             const uint32_t release = tempty_bar + 8 * acc;
-            epilogue_tile(args, job, t_base, job.row0 + int64_t(tm) * BM2 + int64_t(rank) * BM + quarter * 32,
+            epilogue_tile<ST>(args, job, t_base, job.row0 + int64_t(tm) * BM2 + int64_t(rank) * BM + quarter * 32,
                           job.col0 + int64_t(tn) * BN, lane, epi_tile,
                           [release]() { mbar_arrive_cluster(release, 0); }, st, half * (BN / 64), (half + 1) * (BN / 64));
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
@@ -744,6 +799,11 @@ int launch_gram_jobs(const void *operand, bool is_signed, int64_t n, int64_t k_e
     a.num_jobs = num_jobs;
     a.clock_probe = clock_probe;
     a.group_m = (k_extent <= 16384) ? 16 : GROUP_M2_DEFAULT;
+    a.l2_hint = 0;
+    int st_mode = 0;
+    if (const char *e = getenv("AVTEX_GRAM_GROUP")) { const int g = atoi(e); if (g >= 1 && g <= 64) a.group_m = g; }
+    if (const char *e = getenv("AVTEX_GRAM_HINT")) a.l2_hint = atoi(e);
+    if (const char *e = getenv("AVTEX_GRAM_ST")) st_mode = atoi(e);
     int total = 0;
     for (int j = 0; j < num_jobs; ++j) {
         const AvtexGramJob &in = jobs[j];
@@ -780,12 +840,14 @@ int launch_gram_jobs(const void *operand, bool is_signed, int64_t n, int64_t k_e
         // cudaFuncSetAttribute is idempotent: the atomic flag only skips repeats, two racing host threads both succeed
         static std::atomic<bool> attr2_set[64];
         if (device >= 64 || !attr2_set[device].load(std::memory_order_acquire)) {
-            AVTEX_CUDA(cudaFuncSetAttribute(gram_l2_s8_2cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES));
+            AVTEX_CUDA(cudaFuncSetAttribute(gram_l2_s8_2cta_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES));
+            AVTEX_CUDA(cudaFuncSetAttribute(gram_l2_s8_2cta_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES));
             if (device < 64) attr2_set[device].store(true, std::memory_order_release);
         }
         int clusters = sms / 2;
         if (a.num_tiles < clusters) clusters = a.num_tiles;
-        gram_l2_s8_2cta_kernel<<<2 * clusters, NUM_THREADS2, SMEM2_BYTES, as_stream(stream)>>>(map, a);
+        if (st_mode == 1) gram_l2_s8_2cta_kernel<1><<<2 * clusters, NUM_THREADS2, SMEM2_BYTES, as_stream(stream)>>>(map, a);
+        else gram_l2_s8_2cta_kernel<0><<<2 * clusters, NUM_THREADS2, SMEM2_BYTES, as_stream(stream)>>>(map, a);
         AVTEX_LAUNCH_CHECK();
         return 0;
     }

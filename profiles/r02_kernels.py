@@ -67,6 +67,38 @@ elif what == "gram5":
     ms, _ = timed(lambda: engine.gram_l2(pf, 0, rows, symmetric=False, out=D), reps=3)
     ops = 2.0 * rows * 100000 * 12288
     print(f"gram5 {rows} x 100000 K=12288: {ms:.3f} ms  {ops / ms / 1e9:.0f} TOP/s")
+elif what == "gramsym":
+    # symmetric Gram (the single-GPU C5 shape, scaled down): n frames 64x64, K = 12288, direct + transposed stores
+    n = int(sys.argv[2]) if len(sys.argv) > 2 else 40000
+    frames = synth_video_cuda(n, 64, 64, seed=0)
+    pf = engine.pack_frames(frames)
+    D = engine.empty_matrix(n, n, "cuda")
+    ms, _ = timed(lambda: engine.gram_l2(pf, out=D), reps=3)
+    tiles = (-(-n // 256)) * (-(-n // 256) + 1) // 2
+    ops = 2.0 * tiles * 256 * 256 * 12288
+    cfg = " ".join(f"{k}={os.environ[k]}" for k in ("AVTEX_GRAM_GROUP", "AVTEX_GRAM_HINT", "AVTEX_GRAM_ST") if k in os.environ)
+    print(f"gramsym n={n} K=12288 [{cfg}]: {ms:.3f} ms  {ops / ms / 1e9:.0f} TOP/s executed ({tiles} tiles)")
+elif what == "gramjobs":
+    # job list of rank `me` of an 8-rank C5 step, run on ONE GPU: the peer destinations all point at one local scratch
+    # shard, so the time is everything except the NVLink transport of the pushed tiles
+    from audio_video_textures_b200 import dist as D
+    me = int(sys.argv[2]) if len(sys.argv) > 2 else 0
+    world, n, fs, stride = 8, 100000, 40, 4
+    frames = synth_video_cuda(n, 64, 64, seed=0)
+    pf = engine.pack_frames(frames)
+    plans = [D.plan_shards(n, fs, stride, world, r) for r in range(world)]
+    ld = (n + 31) // 32 * 32
+    rows_max = max(p.r_hi - p.r_lo for p in plans)
+    mine = torch.empty((rows_max, ld), dtype=torch.float32, device="cuda")
+    peer = torch.empty((rows_max, ld), dtype=torch.float32, device="cuda")
+    ptrs = [mine.data_ptr() if r == me else peer.data_ptr() for r in range(world)]
+    jobs = D.symmetric_jobs(plans, me, ptrs, ld, stride)
+    tiles = sum((-(-j["rows"] // 256)) * (-(-j["cols"] // 256)) if not j["symmetric"] else
+                (-(-j["rows"] // 256)) * (-(-j["rows"] // 256) + 1) // 2 for j in jobs)
+    for mode in ("push", "nopush"):
+        jl = jobs if mode == "push" else [dict(j, DT=(j["DT"] if j["symmetric"] else None)) for j in jobs]
+        ms, _ = timed(lambda: engine.gram_l2_jobs(pf, jl), reps=5)
+        print(f"gramjobs rank {me}/8 C5 [{mode}]: {ms:.3f} ms  {tiles} tiles  {2.0 * tiles * 65536 * 12288 / ms / 1e9:.0f} TOP/s executed")
 elif what == "fc":
     n = int(sys.argv[2]) if len(sys.argv) > 2 else 20000
     frames = synth_video_cuda(n, 64, 64, seed=0)

@@ -1,0 +1,4 @@
+cd /root/repo
+python -m pytest tests/test_gpu_classic.py tests/test_gpu_virtual.py -x -q -m gpu 2>&1 | tail -2
+python profiles/r02_kernels.py fc 20000
+python profiles/r02_kernels.py fc 25000
