@@ -32,6 +32,8 @@ SIGNATURES = {
     "avtex_sum_nnz": [_p, _i64, _i64, _i64, _p, _p, _int, _p],
     "avtex_diag_filter_pow": [_p, _i64, _i64, _i64, C.POINTER(_f32), _int, _int, _i64, _i64, _i64,
                               _p, _i64, _p, _i64, _f32, _p, _p, _int, _p],
+    "avtex_diag_filter_pow_sym": [_p, _i64, _i64, C.POINTER(_f32), _int, _int, _i64, _p, _i64, _p, _i64, _f32, _p, _p,
+                                  _int, _p],
     "avtex_future_cost_sweep": [_p, _i64, _i64, _i64, _i64, _p, _p, _f32, _p, _p, _int, _p],
     "avtex_future_cost_fused": [_p, _i64, _i64, _f32, _f32, _int, _p, _i64, _p, _p, _p, _int, _p],
     "avtex_pow_matrix": [_p, _i64, _i64, _i64, _f32, _p, _i64, _int, _p],

@@ -37,18 +37,47 @@ struct TapPairs { float2 wp[66]; };
 // the first version stalled on instruction fetch (ncu: stalled_no_instruction was the top reason).
 __device__ __noinline__ float pow_pos_call(float x, float p) { return pow_pos(x, p); }
 
-template <int FS, int S, int FR, bool PACKED>
+// SYM: D1 is symmetric (every distance matrix is), hence so is D2 — bit for bit, because D2[a,b] and D2[b,a] add the
+// same values in the same order.  Only outputs on or above the diagonal are computed (a thread's outputs all have
+// b - a = b0 - a_base, so ownership is per thread; CTAs entirely below the diagonal exit at once) and the strictly
+// upper ones are mirrored through a shared-memory tile so that the mirrored rows are written as 64-byte runs:
+// half the loads, FMAs and pows (stride 1 is FP32-pipe bound) and half the D1 bytes (stride 4 is HBM bound).
+template <int FS, int S, int FR, bool PACKED, bool SYM>
 __global__ void __launch_bounds__(FT)
 diag_filter_kernel(const float *__restrict__ D1, int64_t ld1, int64_t in_row0, int64_t in_rows, const Taps64 taps,
                    const TapPairs pairs, int64_t a0, int64_t rows_out, int64_t m, float *__restrict__ D2, int64_t ld2,
                    float *__restrict__ D3, int64_t ld3, float p, double *sum, unsigned long long *nnz) {
     __shared__ double sred[32];
     __shared__ unsigned long long nred[32];
+    constexpr int TR = FT + FR - 1;                                         // mirrored rows touched by one CTA
+    constexpr int TP = FR + 1;                                              // tile pitch (conflict-free writes)
+    __shared__ float tile2[SYM ? TR * TP : 1];
+    __shared__ float tile3[SYM ? TR * TP : 1];
     constexpr int T = (FR - 1) * S + FS;
     const int64_t n_in = (m - 1) * S + FS;                                  // valid input rows / cols
-    const int64_t a_base = a0 + int64_t(blockIdx.y) * FR;                   // first output row of the band
-    const int64_t b_blk = int64_t(blockIdx.x) * FT - (FR - 1);              // output col of thread 0's output 0
+    int bx = blockIdx.x, by = blockIdx.y;
+    if (SYM) {
+        // Band y needs the column blocks x >= y / (FT / FR) only (the others lie below the diagonal).  The grid is the
+        // triangle folded in two: grid row f serves band f with its first n1 CTAs and band GY-1-f with the rest, so
+        // hardly any CTA is launched just to exit.
+        constexpr int R = FT / FR;
+        const int GX = int((m + FR - 1 + FT - 1) / FT), GY = int((rows_out + FR - 1) / FR);
+        const int y2 = GY - 1 - by, n1 = GX - by / R;
+        if (bx < n1) {
+            bx += by / R;
+        } else {
+            bx -= n1;
+            if (y2 <= by || bx >= GX - y2 / R) return;
+            bx += y2 / R;
+            by = y2;
+        }
+    }
+    const int64_t a_base = a0 + int64_t(by) * FR;                           // first output row of the band
+    const int64_t b_blk = int64_t(bx) * FT - (FR - 1);                      // output col of thread 0's output 0
+    if (SYM && b_blk + FT + FR - 2 < a_base) return;                        // the whole CTA lies below the diagonal
     const int64_t b0 = b_blk + threadIdx.x;
+    const bool owner = !SYM || b0 >= a_base;                                // this thread's outputs have b >= a
+    const bool mirror = SYM && b0 > a_base;                                 // ... b > a: also stored as D2[b, a]
     const int64_t grow = a_base * S;                                        // global input row at t = 0
     const int64_t gcol = b0 * S;
     const float *src = D1 + (grow - in_row0) * ld1 + gcol;
@@ -60,11 +89,12 @@ diag_filter_kernel(const float *__restrict__ D1, int64_t ld1, int64_t in_row0, i
     // those on the matrix border)
     const bool interior = (b_blk * S >= 0) && ((b_blk + FT - 1) * S + T - 1 < n_in) &&
                           (grow + T - 1 < in_row0 + in_rows) && (grow + T - 1 < n_in);
-    if (interior && PACKED) {
+    if (!owner) {
+        // nothing to compute: the mirror image of these outputs is owned by another CTA
+    } else if (interior && PACKED) {
         // Packed fp32x2 FMA (Blackwell FFMA2): outputs 2p and 2p+1 share one instruction.  At step t they
-        // need taps q = t - 2p and q - 1, so the pair (w[q], w[q-1]) is kept as one 64-bit register value
-        // (zero outside [0, FS)).  Same operation order per output as the scalar path -> identical bits,
-        // half the FMA issue slots (this kernel is issue-bound at stride 1: 40 FMAs + pow per output).
+        // need taps q = t - 2p and q - 1: the pair (w[q], w[q-1]) comes from the host-built TapPairs (zero outside
+        // [0, FS)).  Same operation order per output as the scalar path -> identical bits, half the FMA issue slots.
         float2 acc2[FR / 2];
 #pragma unroll
         for (int p2 = 0; p2 < FR / 2; ++p2) acc2[p2] = make_float2(0.f, 0.f);
@@ -109,18 +139,22 @@ diag_filter_kernel(const float *__restrict__ D1, int64_t ld1, int64_t in_row0, i
     int z = 0;
     float *o2 = D2 + (a_base - a0) * ld2 + b0;
     float *o3 = (D3 != nullptr) ? D3 + (a_base - a0) * ld3 + b0 : nullptr;
+    float *m2 = tile2 + threadIdx.x * TP, *m3 = tile3 + threadIdx.x * TP;   // element i of this thread -> tile[tid + i][i]
     // CTA-uniform: every output of every thread is inside the matrix -> no per-output range checks, pow inlined
     // (the hot path then is ~16 KB of straight-line code; border CTAs keep the out-of-line pow)
     const bool all_out = interior && (a_base + FR <= a0 + rows_out) && (b_blk >= 0) && (b_blk + FT + FR - 2 < m);
-    if (all_out) {
+    if (!owner) {
+    } else if (all_out) {
         const int64_t st2 = ld2 + 1, st3 = ld3 + 1;
         if (o3 != nullptr) {
 #pragma unroll
             for (int i = 0; i < FR; ++i) {
+                const float pw = pow_pos(acc[i], p);
                 *o2 = acc[i];
-                *o3 = pow_pos(acc[i], p);
+                *o3 = pw;
                 o2 += st2;
                 o3 += st3;
+                if (SYM) { m2[i * (TP + 1)] = acc[i]; m3[i * (TP + 1)] = pw; }
                 s += acc[i];
                 z += (acc[i] != 0.f);
             }
@@ -129,6 +163,7 @@ diag_filter_kernel(const float *__restrict__ D1, int64_t ld1, int64_t in_row0, i
             for (int i = 0; i < FR; ++i) {
                 *o2 = acc[i];
                 o2 += st2;
+                if (SYM) m2[i * (TP + 1)] = acc[i];
                 s += acc[i];
                 z += (acc[i] != 0.f);
             }
@@ -139,9 +174,45 @@ diag_filter_kernel(const float *__restrict__ D1, int64_t ld1, int64_t in_row0, i
             const int64_t a = a_base + i, b = b0 + i;
             if (a < a0 + rows_out && b >= 0 && b < m) {
                 o2[i * (ld2 + 1)] = acc[i];
-                if (o3 != nullptr) o3[i * (ld3 + 1)] = pow_pos_call(acc[i], p);
+                if (SYM) m2[i * (TP + 1)] = acc[i];
+                if (o3 != nullptr) {
+                    const float pw = pow_pos_call(acc[i], p);
+                    o3[i * (ld3 + 1)] = pw;
+                    if (SYM) m3[i * (TP + 1)] = pw;
+                }
                 s += acc[i];
                 z += (acc[i] != 0.f);
+            }
+        }
+    }
+    if (SYM) {
+        if (mirror) { s *= 2.f; z *= 2; }                                   // the mirrored copies count too
+        __syncthreads();
+        // mirrored rows b = b_blk + r, columns a_base .. a_base + FR - 1: element i of row r came from thread r - i
+        const int64_t a_end = a0 + rows_out;
+        const bool vec_ok = (ld2 % 4 == 0) && (ld3 % 4 == 0) && (FR % 4 == 0) &&
+                            (((reinterpret_cast<uintptr_t>(D2) | reinterpret_cast<uintptr_t>(D3)) & 15) == 0);
+        for (int idx = threadIdx.x; idx < TR * (FR / 4); idx += FT) {
+            const int r = idx / (FR / 4), i0 = (idx % (FR / 4)) * 4;
+            const int64_t b = b_blk + r;
+            if (b < 0 || b >= m) continue;
+            const float *t2 = tile2 + r * TP + i0, *t3 = tile3 + r * TP + i0;
+            float *d2 = D2 + (b - a0) * ld2 + a_base + i0;
+            float *d3 = (D3 != nullptr) ? D3 + (b - a0) * ld3 + a_base + i0 : nullptr;
+            const bool full = vec_ok && (r - (i0 + 3) >= 0) && (r - i0 < FT) && (b - (i0 + 3) > a_base) &&
+                              (a_base + i0 + 3 < a_end);
+            if (full) {
+                *reinterpret_cast<float4 *>(d2) = make_float4(t2[0], t2[1], t2[2], t2[3]);
+                if (d3 != nullptr) *reinterpret_cast<float4 *>(d3) = make_float4(t3[0], t3[1], t3[2], t3[3]);
+            } else {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int i = i0 + e;
+                    if (r - i >= 0 && r - i < FT && b - i > a_base && a_base + i < a_end) {
+                        d2[e] = t2[e];
+                        if (d3 != nullptr) d3[e] = t3[e];
+                    }
+                }
             }
         }
     }
@@ -186,19 +257,31 @@ template <int S> constexpr int filter_r() { return S == 1 ? 16 : 8; }
 template <int FS, int S, int FR = filter_r<S>()>
 void launch_fast(const float *D1, int64_t ld1, int64_t in_row0, int64_t in_rows, const float *h_w, int64_t a0,
                  int64_t rows_out, int64_t m, float *D2, int64_t ld2, float *D3, int64_t ld3, float p,
-                 double *sum, unsigned long long *nnz, cudaStream_t st) {
+                 double *sum, unsigned long long *nnz, bool symmetric, cudaStream_t st) {
     Taps64 taps;
     for (int i = 0; i < 64; ++i) taps.w[i] = (i < FS) ? h_w[i] : 0.f;
     TapPairs pairs;
     for (int q = 0; q < 66; ++q) pairs.wp[q] = make_float2(q < FS ? h_w[q] : 0.f, (q >= 1 && q <= FS) ? h_w[q - 1] : 0.f);
     dim3 grid((unsigned)((m + FR - 1 + FT - 1) / FT), (unsigned)((rows_out + FR - 1) / FR));
     static const bool packed_off = []() { const char *e = getenv("AVTEX_FILTER_FFMA2"); return e != nullptr && e[0] == '0'; }();
-    if (S == 1 && !packed_off)
-        diag_filter_kernel<FS, S, FR, S == 1><<<grid, FT, 0, st>>>(D1, ld1, in_row0, in_rows, taps, pairs, a0, rows_out, m, D2, ld2, D3,
-                                                           ld3, p, sum, nnz);
-    else
-    diag_filter_kernel<FS, S, FR, false><<<grid, FT, 0, st>>>(D1, ld1, in_row0, in_rows, taps, pairs, a0, rows_out, m, D2, ld2, D3,
-                                                   ld3, p, sum, nnz);
+#define AVTEX_FILTER_LAUNCH(PACKED_, SYM_)                                                                         \
+    diag_filter_kernel<FS, S, FR, PACKED_, SYM_><<<grid, FT, 0, st>>>(D1, ld1, in_row0, in_rows, taps, pairs, a0, rows_out, m, \
+                                                                    D2, ld2, D3, ld3, p, sum, nnz)
+    const bool packed = (S == 1) && !packed_off;
+    if (symmetric) {                                                 // folded triangle (see the kernel)
+        static_assert(FT % FR == 0, "the symmetric grid needs FT to be a multiple of FR");
+        const int GX = (int)grid.x, GY = (int)grid.y, R = FT / FR;
+        int w = 0;
+        for (int f = 0; f < (GY + 1) / 2; ++f) {
+            const int y2 = GY - 1 - f;
+            const int n = (GX - f / R) + (y2 > f ? (GX - y2 / R > 0 ? GX - y2 / R : 0) : 0);
+            w = n > w ? n : w;
+        }
+        grid = dim3((unsigned)w, (unsigned)((GY + 1) / 2));
+    }
+    if (symmetric) { if (packed) AVTEX_FILTER_LAUNCH(S == 1, true); else AVTEX_FILTER_LAUNCH(false, true); }
+    else           { if (packed) AVTEX_FILTER_LAUNCH(S == 1, false); else AVTEX_FILTER_LAUNCH(false, false); }
+#undef AVTEX_FILTER_LAUNCH
 }
 
 // out = D ** p elementwise (classic/q_learning.py:34 when D2 comes from the caller, not from the fused filter).
@@ -233,10 +316,11 @@ extern "C" int avtex_pow_matrix(const float *D, int64_t ld, int64_t rows, int64_
     return 0;
 }
 
-extern "C" int avtex_diag_filter_pow(const float *D1, int64_t ld1, int64_t in_row0, int64_t in_rows, const float *h_w,
-                                     int fs, int stride, int64_t a0, int64_t rows_out, int64_t m,
-                                     float *D2, int64_t ld2, float *D3, int64_t ld3, float p,
-                                     double *sum, unsigned long long *nnz, int device, void *stream) {
+namespace {
+
+int diag_filter_impl(const float *D1, int64_t ld1, int64_t in_row0, int64_t in_rows, const float *h_w, int fs, int stride,
+                     int64_t a0, int64_t rows_out, int64_t m, float *D2, int64_t ld2, float *D3, int64_t ld3, float p,
+                     double *sum, unsigned long long *nnz, bool symmetric, int device, void *stream) {
     AVTEX_ENTER(device);
     AVTEX_REQUIRE(fs >= 1 && fs <= 960 && stride >= 1, "diag_filter: fs=%d stride=%d unsupported", fs, stride);
     AVTEX_REQUIRE(m >= 1 && rows_out >= 1 && a0 >= 0 && a0 + rows_out <= m && ld2 >= m,
@@ -249,16 +333,14 @@ extern "C" int avtex_diag_filter_pow(const float *D1, int64_t ld1, int64_t in_ro
                   (long long)(in_row0 + in_rows));
     AVTEX_REQUIRE((sum == nullptr) == (nnz == nullptr), "diag_filter: sum and nnz go together");
     AVTEX_REQUIRE(D3 == nullptr || ld3 >= m, "diag_filter: ld3 too small");
+    AVTEX_REQUIRE(!symmetric || (a0 == 0 && rows_out == m && in_row0 == 0),
+                  "diag_filter: the symmetric form needs the whole matrix (a0 = 0, rows_out = m, in_row0 = 0)");
     cudaStream_t st = as_stream(stream);
     const int key = fs * 100 + stride;
-    static const int r_exp = []() { const char *e = getenv("AVTEX_FILTER_R"); return e ? atoi(e) : 0; }();
 #define AVTEX_FAST(FS_, S_)                                                                            \
     case FS_ * 100 + S_:                                                                               \
         AVTEX_REQUIRE((rows_out + filter_r<S_>() - 1) / filter_r<S_>() <= 65535, "diag_filter: too many row bands"); \
-        if (S_ == 1 && FS_ == 40 && r_exp == 32)                                                       \
-            launch_fast<FS_, S_, (S_ == 1 && FS_ == 40) ? 32 : filter_r<S_>()>(D1, ld1, in_row0, in_rows, h_w, a0, rows_out, m, D2, ld2, D3, ld3, p, sum, nnz, st); \
-        else                                                                                           \
-        launch_fast<FS_, S_>(D1, ld1, in_row0, in_rows, h_w, a0, rows_out, m, D2, ld2, D3, ld3, p, sum, nnz, st); \
+        launch_fast<FS_, S_>(D1, ld1, in_row0, in_rows, h_w, a0, rows_out, m, D2, ld2, D3, ld3, p, sum, nnz, symmetric, st); \
         break;
     switch (key) {
         AVTEX_FAST(40, 1)
@@ -266,7 +348,7 @@ extern "C" int avtex_diag_filter_pow(const float *D1, int64_t ld1, int64_t in_ro
         AVTEX_FAST(16, 1)
         AVTEX_FAST(16, 4)
         AVTEX_FAST(8, 1)
-        default: {
+        default: {                                                   // any (fs, stride): no symmetric shortcut
             TapsBig taps;
             for (int i = 0; i < 960; ++i) taps.w[i] = (i < fs) ? h_w[i] : 0.f;
             for (int64_t r = 0; r < rows_out; r += 65535) {          // gridDim.y <= 65535: row bands of that many rows
@@ -281,4 +363,21 @@ extern "C" int avtex_diag_filter_pow(const float *D1, int64_t ld1, int64_t in_ro
 #undef AVTEX_FAST
     AVTEX_LAUNCH_CHECK();
     return 0;
+}
+
+}  // namespace
+
+extern "C" int avtex_diag_filter_pow(const float *D1, int64_t ld1, int64_t in_row0, int64_t in_rows, const float *h_w,
+                                     int fs, int stride, int64_t a0, int64_t rows_out, int64_t m,
+                                     float *D2, int64_t ld2, float *D3, int64_t ld3, float p,
+                                     double *sum, unsigned long long *nnz, int device, void *stream) {
+    return diag_filter_impl(D1, ld1, in_row0, in_rows, h_w, fs, stride, a0, rows_out, m, D2, ld2, D3, ld3, p, sum, nnz,
+                            false, device, stream);
+}
+
+extern "C" int avtex_diag_filter_pow_sym(const float *D1, int64_t ld1, int64_t n_rows, const float *h_w, int fs, int stride,
+                                         int64_t m, float *D2, int64_t ld2, float *D3, int64_t ld3, float p,
+                                         double *sum, unsigned long long *nnz, int device, void *stream) {
+    return diag_filter_impl(D1, ld1, 0, n_rows, h_w, fs, stride, 0, m, m, D2, ld2, D3, ld3, p, sum, nnz, true, device,
+                            stream);
 }

@@ -186,6 +186,8 @@ def gram_l2(pf: PackedFrames, row0: int = 0, rows: int | None = None, symmetric:
     else:
         _lib.call("avtex_gram_l2_u8", _lib.ptr(pf.packed), n, pf.k, pf.packed.stride(0), _lib.ptr(pf.sqnorm),
                   row0, rows, 1 if symmetric else 0, _lib.ptr(D), D.stride(0), s, z, _dev(D), _stream(D))
+    if symmetric:
+        mark_symmetric(D)
     return D
 
 
@@ -279,6 +281,7 @@ def pairwise_l2_from_host(frames: torch.Tensor, device=None, stats: torch.Tensor
             t.record_stream(copy_stream)
     elif kp * 128 * 128 < GRAM_MAX_SQNORM:
         pf._checked = (True, "")
+    mark_symmetric(D1)
     return D1, pf
 
 
@@ -398,25 +401,60 @@ def filtered_size(n: int, filter_size: int, stride: int) -> int:
     return (n - filter_size) // stride + 1
 
 
+# Distance matrices this module produced itself (symmetric by construction: the Gram epilogue stores D[r,c] and
+# D[c,r] from the same register) are remembered by object identity + torch's in-place version counter, so that K2
+# may use its symmetric form without the caller promising anything.  A matrix that was modified in place, copied,
+# re-sliced or supplied by the user is simply not found and takes the general kernel.
+_SYMMETRIC: list = []
+
+
+def mark_symmetric(t: torch.Tensor) -> torch.Tensor:
+    import weakref
+    _SYMMETRIC[:] = [e for e in _SYMMETRIC[-15:] if e[0]() is not None]
+    _SYMMETRIC.append((weakref.ref(t), t._version, t.data_ptr(), tuple(t.shape), t.stride()))
+    return t
+
+
+def known_symmetric(t: torch.Tensor) -> bool:
+    for ref, ver, ptr, shape, stride in _SYMMETRIC:
+        if ref() is t and t._version == ver and t.data_ptr() == ptr and tuple(t.shape) == shape and t.stride() == stride:
+            return True
+    return False
+
+
 def diag_filter(D1: torch.Tensor, filter_size: int, stride: int = 1, p: float | None = None,
                 m: int | None = None, a0: int = 0, rows_out: int | None = None, in_row0: int = 0,
-                stats: torch.Tensor | None = None, taps: np.ndarray | None = None):
+                stats: torch.Tensor | None = None, taps: np.ndarray | None = None, symmetric: bool | None = None):
     """K2.  D1 holds global rows [in_row0, in_row0 + D1.shape[0]) and all columns.
-    Returns (D2[rows_out, m], D3 | None)."""
+    Returns (D2[rows_out, m], D3 | None).
+    symmetric: D1 == D1.T bit for bit (the whole square matrix): only the upper triangle is computed and mirrored
+    (half the D1 bytes, FMAs and pows).  None = yes iff D1 is a distance matrix this module produced
+    (`known_symmetric`); row shards and caller-supplied matrices take the general kernel."""
     n_cols = D1.shape[1]
     m = filtered_size(n_cols, filter_size, stride) if m is None else m
     rows_out = m - a0 if rows_out is None else rows_out
     taps = binomial_taps(filter_size) if taps is None else np.ascontiguousarray(taps, dtype=np.float32)
     if taps.shape[0] != filter_size:
         raise ValueError("taps length != filter_size")
+    whole = (a0 == 0 and rows_out == m and in_row0 == 0 and D1.shape[0] == n_cols)
+    if symmetric is None:
+        symmetric = whole and known_symmetric(D1)
+    elif symmetric and not whole:
+        raise ValueError("symmetric=True needs the whole square matrix")
     D2 = empty_matrix(rows_out, m, D1.device)
     D3 = empty_matrix(rows_out, m, D1.device) if p is not None else None
     s, z = _stats_ptrs(stats)
-    _lib.call("avtex_diag_filter_pow", _lib.ptr(D1), D1.stride(0), in_row0, D1.shape[0],
-              taps.ctypes.data_as(C.POINTER(C.c_float)), filter_size, stride, a0, rows_out, m,
-              _lib.ptr(D2), D2.stride(0), _lib.ptr(D3), D3.stride(0) if D3 is not None else 0,
-              C.c_float(_f32(p if p is not None else 1.0)), s, z,
-              _dev(D1), _stream(D1))
+    tp = taps.ctypes.data_as(C.POINTER(C.c_float))
+    pf = C.c_float(_f32(p if p is not None else 1.0))
+    if symmetric:
+        _lib.call("avtex_diag_filter_pow_sym", _lib.ptr(D1), D1.stride(0), D1.shape[0], tp, filter_size, stride, m,
+                  _lib.ptr(D2), D2.stride(0), _lib.ptr(D3), D3.stride(0) if D3 is not None else 0, pf, s, z,
+                  _dev(D1), _stream(D1))
+        mark_symmetric(D2)
+    else:
+        _lib.call("avtex_diag_filter_pow", _lib.ptr(D1), D1.stride(0), in_row0, D1.shape[0], tp, filter_size, stride,
+                  a0, rows_out, m, _lib.ptr(D2), D2.stride(0), _lib.ptr(D3), D3.stride(0) if D3 is not None else 0,
+                  pf, s, z, _dev(D1), _stream(D1))
     return D2, D3
 
 

@@ -324,9 +324,15 @@ def hbm_rooflines(dev, peaks):
     pf = engine.pack_frames(frames)
     D1 = engine.gram_l2(pf)
     m = engine.filtered_size(n, fs, 1)
-    ms, (D2, D3) = timed(lambda: engine.diag_filter(D1, fs, 1, p=0.7))
-    line("diag_filter_kernel<40,1,16> (stride 1; FP32-pipe bound, see DESIGN 4.2)", 4.0 * n * n + 8.0 * m * m, ms,
-         f"K2 -m 1/2: read D1 {n}^2, write D2 + D3 {m}^2")
+    ms, (D2, D3) = timed(lambda: engine.diag_filter(D1, fs, 1, p=0.7, symmetric=False))
+    line("diag_filter_kernel<40,1,16,general> (stride 1; FP32-pipe bound, see DESIGN 4.2)", 4.0 * n * n + 8.0 * m * m, ms,
+         f"K2 -m 1/2, any D1: read D1 {n}^2, write D2 + D3 {m}^2")
+    del D2, D3
+    ms, (D2, D3) = timed(lambda: engine.diag_filter(D1, fs, 1, p=0.7, symmetric=True))
+    line("diag_filter_kernel<40,1,16,symmetric> (stride 1; the form compute_D2 uses on compute_D1's matrix)",
+         2.0 * n * n + 8.0 * m * m, ms,
+         f"K2 -m 1/2, symmetric D1: read the upper triangle of D1 {n}^2, write D2 + D3 {m}^2 "
+         f"(= {(4.0 * n * n + 8.0 * m * m) / (ms * 1e-3) / 1e9 / peaks['hbm_gbs']:.3f} of HBM counted in the general kernel's bytes)")
     del D2
     mv = torch.zeros((m + 31) // 32 * 32, dtype=torch.float32, device=dev)
     out_m = torch.empty_like(mv)

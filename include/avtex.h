@@ -152,6 +152,17 @@ AVTEX_API int avtex_diag_filter_pow(const float *D1, int64_t ld1, int64_t in_row
                           int stride, int64_t a0, int64_t rows_out, int64_t m,
                           float *D2, int64_t ld2, float *D3, int64_t ld3, float p,
                           double *sum, unsigned long long *nnz, int device, void *stream);
+
+/* The same filter for a SYMMETRIC D1 (D1[i,j] == D1[j,i] bit for bit, as every matrix written by avtex_gram_l2_* is):
+ * D2 is then symmetric too — both mirror images add the same values in the same order — so only the outputs on or
+ * above the diagonal are computed and the strictly upper ones are mirrored through shared memory (64-byte runs).
+ * Half the D1 bytes (stride 4 is HBM-bound), half the FMAs and pows (stride 1 is FP32-pipe bound); results are
+ * bit-identical to avtex_diag_filter_pow on the same input.  Whole matrix only: D1 is [n_rows >= (m-1)*stride+fs, ld1],
+ * D2 / D3 are [m, ld].  fs/stride pairs without a register-resident instantiation fall back to the general kernel.
+ * replaces: classic/computeD2.py:34-42 + classic/q_learning.py:34 when D1 comes from compute_D1. */
+AVTEX_API int avtex_diag_filter_pow_sym(const float *D1, int64_t ld1, int64_t n_rows, const float *h_w, int fs, int stride,
+                              int64_t m, float *D2, int64_t ld2, float *D3, int64_t ld3, float p,
+                              double *sum, unsigned long long *nnz, int device, void *stream);
 /* out = D ** p elementwise (D >= 0, p > 0), same pow as the fused epilogue above.
  * replaces: `D3 = D2 ** p` of classic/q_learning.py:34 when D2 is handed in by the caller. */
 AVTEX_API int avtex_pow_matrix(const float *D, int64_t ld, int64_t rows, int64_t cols, float p, float *out,

@@ -43,6 +43,32 @@ if what == "filter1":
         ms, _ = timed(lambda: engine.diag_filter(D1, 40, 1, p=0.7, stats=st))
         b = 4.0 * n * n + 8.0 * m * m
         print(f"filter1 N={n} stats={stats} s1={os.environ.get('AVTEX_FILTER_S1', '1')}: {ms:.3f} ms  {b / ms / 1e6:.0f} GB/s  {b / ms / 1e6 / HBM:.3f} of HBM")
+elif what == "filter1s":
+    # symmetric form of the stride-1 filter (D1 produced by the Gram kernel: known symmetric)
+    n = int(sys.argv[2]) if len(sys.argv) > 2 else 16000
+    A = torch.empty((n, n), dtype=torch.float32, device="cuda").uniform_(100.0, 20000.0)
+    D1 = engine.empty_matrix(n, n, "cuda")
+    D1.copy_(torch.triu(A) + torch.triu(A, 1).T)
+    del A
+    m = n - 39
+    for stats in (False, True):
+        st = engine.new_stats("cuda") if stats else None
+        ms, _ = timed(lambda: engine.diag_filter(D1, 40, 1, p=0.7, stats=st, symmetric=True))
+        b_full, b_sym = 4.0 * n * n + 8.0 * m * m, 2.0 * n * n + 8.0 * m * m
+        print(f"filter1 SYMMETRIC N={n} stats={stats}: {ms:.3f} ms  {b_sym / ms / 1e6:.0f} GB/s of the bytes it needs "
+              f"({b_sym / ms / 1e6 / HBM:.3f} of HBM); against the general kernel's bytes {b_full / ms / 1e6 / HBM:.3f}")
+elif what == "filter4s":
+    # symmetric form, stride 4, the single-GPU C5 shape scaled to 40000 frames
+    n = 40000
+    A = torch.empty((n, n), dtype=torch.float32, device="cuda").uniform_(100.0, 20000.0)
+    D1 = engine.empty_matrix(n, n, "cuda")
+    D1.copy_(torch.triu(A) + torch.triu(A, 1).T)
+    del A
+    m = (n - 40) // 4 + 1
+    for sym in (False, True):
+        ms, _ = timed(lambda: engine.diag_filter(D1, 40, 4, p=0.7, symmetric=sym))
+        b = (2.0 if sym else 4.0) * n * n + 8.0 * m * m
+        print(f"filter4 N={n} symmetric={sym}: {ms:.3f} ms  {b / ms / 1e6:.0f} GB/s  {b / ms / 1e6 / HBM:.3f} of HBM (own bytes)")
 elif what == "filter4":
     rows, n = 12576, 100000
     D1 = torch.empty((rows, n), dtype=torch.float32, device="cuda").uniform_(100.0, 20000.0)

@@ -229,6 +229,37 @@ def test_diag_filter_generic_and_edge(eng, fs, stride, n):
     np.testing.assert_allclose(D2.cpu().numpy(), ref.numpy(), rtol=1e-5)
 
 
+@pytest.mark.parametrize("fs,stride,n", [(40, 1, 300), (40, 1, 777), (40, 4, 1241), (40, 4, 523), (16, 1, 130),
+                                         (16, 4, 401), (8, 1, 64), (40, 1, 41), (40, 4, 40), (5, 2, 61)])
+def test_diag_filter_symmetric_form_is_bit_identical(eng, fs, stride, n):
+    """K2's symmetric form (upper triangle computed, mirrored through shared memory) against the general kernel on
+    a symmetric D1: D2 and D3 bit for bit, nnz equal, sum to fp32-partial accuracy.  Also: the automatic choice
+    (`known_symmetric`) only fires for matrices the engine produced and drops out after an in-place edit."""
+    gen = torch.Generator().manual_seed(fs * 1000 + stride * 10 + n)
+    A = torch.rand(n, n, generator=gen) * 3000
+    D1 = eng.empty_matrix(n, n, "cuda")
+    D1.copy_(((A + A.T) / 2).fill_diagonal_(0.0))
+    assert torch.equal(D1, D1.T)
+    st_g, st_s = eng.new_stats("cuda"), eng.new_stats("cuda")
+    G2, G3 = eng.diag_filter(D1, fs, stride, p=0.7, stats=st_g, symmetric=False)
+    S2, S3 = eng.diag_filter(D1, fs, stride, p=0.7, stats=st_s, symmetric=True)
+    assert torch.equal(G2, S2) and torch.equal(G3, S3)
+    assert torch.equal(S2, S2.T)
+    (tg, zg), (ts, zs) = eng.read_stats(st_g), eng.read_stats(st_s)
+    assert zg == zs
+    np.testing.assert_allclose(ts, tg, rtol=1e-6)
+    S2only, none = eng.diag_filter(D1, fs, stride, symmetric=True)
+    assert none is None and torch.equal(S2only, G2)
+    # automatic choice
+    assert not eng.known_symmetric(D1)                      # filled by the caller: unknown provenance
+    frames = torch.randint(0, 256, (max(n, 64), 8, 8, 3), dtype=torch.uint8, generator=gen).cuda()
+    Dg = eng.gram_l2(eng.pack_frames(frames))
+    assert eng.known_symmetric(Dg) and torch.equal(Dg, Dg.T)
+    assert not eng.known_symmetric(Dg[:-1])                 # another view: not recognised
+    Dg[0, 1] += 1.0
+    assert not eng.known_symmetric(Dg)                      # modified in place: no longer trusted
+
+
 def test_fused_pow_accuracy(eng):
     """D3 = D2 ** p is evaluated by a split-exponent exp2/log2 (common.cuh: pow_pos) instead of powf;
     it must stay within a few ulp of the exact power over the whole dynamic range, incl. 0."""
