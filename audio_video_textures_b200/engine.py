@@ -339,19 +339,58 @@ def transition_probs(D: torch.Tensor, sigma, shift: int = 1, rows_out: int | Non
     return P, Pn, counts
 
 
+_PINNED: dict = {}
+
+
+def _pinned(nbytes: int) -> torch.Tensor:
+    """A cached page-locked staging buffer of at least nbytes (grown geometrically, one per process)."""
+    buf = _PINNED.get("buf")
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(nbytes, 2 * (buf.numel() if buf is not None else 0), 1 << 20), dtype=torch.uint8,
+                          pin_memory=True)
+        _PINNED["buf"] = buf
+    return buf
+
+
 def csr_from_matrix(P: torch.Tensor, counts: torch.Tensor | None = None):
-    """Ascending non-zero columns per row -> (rowptr int64 numpy, colidx int32 numpy).  One sync."""
+    """Ascending non-zero columns per row -> (rowptr int64 numpy, colidx int32 numpy).
+    Matrices up to 16 MB (M <= 2048) are compacted into a full-capacity index buffer and brought to the host with
+    ONE asynchronous copy into page-locked memory and one sync (a pageable `.cpu()` of the 3 MB list plus the
+    `.item()` needed to size it cost 1.5 ms at C2, more than the whole device pass); larger ones size the list first."""
     rows, cols = P.shape
+    dev = P.device
     if counts is None:
-        counts = torch.empty(rows, dtype=torch.int32, device=P.device)
+        counts = torch.empty(rows, dtype=torch.int32, device=dev)
         _lib.call("avtex_row_nnz", _lib.ptr(P), P.stride(0), rows, cols, _lib.ptr(counts), _dev(P), _stream(P))
-    rowptr = torch.zeros(rows + 1, dtype=torch.int64, device=P.device)
+    cap = rows * cols
+    small = cap * 4 <= (16 << 20)
+    head = (rows + 1) * 8
+    if small:
+        # [rowptr int64 (rows + 1) | colidx int32 (capacity)] in one device buffer
+        both = torch.empty(head + cap * 4, dtype=torch.uint8, device=dev)
+        rowptr = both[:head].view(torch.int64)
+        colidx = both[head:].view(torch.int32)
+        rowptr[0] = 0
+        torch.cumsum(counts, 0, out=rowptr[1:])
+        _lib.call("avtex_csr_fill", _lib.ptr(P), P.stride(0), rows, cols, _lib.ptr(rowptr), _lib.ptr(colidx),
+                  _dev(P), _stream(P))
+        host = _pinned(both.numel())[:both.numel()]
+        host.copy_(both, non_blocking=True)
+        torch.cuda.current_stream(dev).synchronize()
+        rp = host[:head].view(torch.int64).numpy().copy()
+        total = int(rp[-1])
+        return rp, host[head:head + total * 4].view(torch.int32).numpy().copy()
+    rowptr = torch.zeros(rows + 1, dtype=torch.int64, device=dev)
     torch.cumsum(counts, 0, out=rowptr[1:])
     total = int(rowptr[-1].item())
-    colidx = torch.empty(max(total, 1), dtype=torch.int32, device=P.device)
+    colidx = torch.empty(max(total, 1), dtype=torch.int32, device=dev)
     _lib.call("avtex_csr_fill", _lib.ptr(P), P.stride(0), rows, cols, _lib.ptr(rowptr), _lib.ptr(colidx),
               _dev(P), _stream(P))
-    return rowptr.cpu().numpy(), colidx[:total].cpu().numpy()
+    host = _pinned(head + total * 4)
+    host[:head].copy_(rowptr.view(torch.uint8), non_blocking=True)
+    host[head:head + total * 4].copy_(colidx[:total].view(torch.uint8), non_blocking=True)
+    torch.cuda.current_stream(dev).synchronize()
+    return host[:head].view(torch.int64).numpy().copy(), host[head:head + total * 4].view(torch.int32).numpy().copy()
 
 
 class SurvivorRows:
