@@ -9,14 +9,15 @@
 // kernel parameters (constant-bank FFMA operands: no shared-memory or LDS traffic at all).  Within
 // a warp consecutive threads own consecutive diagonals, so every load is a coalesced row segment.
 //
-// Stride 1 (-m 1 / -m 2) is bound by the FP32 pipe, not by HBM: 40 FMAs per output = 0.32 ms of pure FMA-pipe time
-// at N = 16000 against 0.47 ms of HBM time, plus ~45 instructions per output of loads / pow / stores / statistics;
-// this kernel runs at 89 % issue utilisation there (1.11 ms, 0.42 of the HBM roofline).  Round 2 tried the
-// shared-memory staged sliding-window design the north star names (cp.async ring, one LDS + 20.5 FFMA2 per
-// output, tap pairs in registers; also a warp-specialised form with setmaxnreg): both were correct and
-// bit-identical but SLOWER (1.28 - 1.40 ms) — 124 live tap / accumulator registers leave 12-16 warps per SM and
-// the write-out code dominates; FFMA2 halves issue slots, not FP32-pipe cycles.  The experiment (source, ncu
-// captures, analysis) is kept under profiles/r02_filter_sliding_window_experiment.*; DESIGN.md §4.2.
+// Stride 1 (-m 1 / -m 2) is bound by the FP32 pipe and instruction issue, not by HBM: 40 FMAs per output = 0.32 ms of
+// pure FMA-pipe time at N = 16000 against 0.47 ms of HBM time.  Round 2: (1) the FFMA2 tap pairs are built on the HOST
+// and passed as aligned kernel parameters (TapPairs) — assembling them in the kernel cost two UMOVs per odd pair, more
+// feeding instructions than FMAs; (2) a CTA-uniform all-outputs-inside path without range checks, pow inlined:
+// 1151 M -> 697 M warp instructions, 1.11 -> 0.75 ms (0.42 -> 0.62 of the HBM roofline); (3) the SYMMETRIC form below
+// halves the work when D1 is a distance matrix (0.64-0.69 ms at stride 1, 1.67x at stride 4).  The shared-memory staged
+// sliding-window design the north star names (cp.async ring, tap pairs in registers, also warp-specialised) was
+// built, bit-identical, and SLOWER (1.28-1.40 ms: 124 live registers leave 12-16 warps per SM); archived under
+// profiles/r02_filter_sliding_window_experiment.*; DESIGN.md §4.2.
 #include <stdlib.h>
 
 #include "common.cuh"

@@ -652,6 +652,7 @@ class VirtualBox:
 
 def virtual_survivors(results: list):
     """CSR of P3_new assembled from the virtual ranks' shards."""
-    ptrs, cols = zip(*(engine.csr_from_matrix(r.P3_new, r.counts) for r in results))
+    # csr_from_matrix returns views of a small ring of page-locked buffers: copy, more shards than buffers may follow
+    ptrs, cols = zip(*((rp.copy(), ci.copy()) for rp, ci in (engine.csr_from_matrix(r.P3_new, r.counts) for r in results)))
     counts = np.concatenate([np.diff(p) for p in ptrs])
     return np.concatenate(([0], np.cumsum(counts))).astype(np.int64), np.concatenate(cols)

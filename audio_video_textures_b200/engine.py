@@ -339,24 +339,29 @@ def transition_probs(D: torch.Tensor, sigma, shift: int = 1, rows_out: int | Non
     return P, Pn, counts
 
 
-_PINNED: dict = {}
+_PINNED: dict = {"ring": [None] * 4, "next": 0}
 
 
 def _pinned(nbytes: int) -> torch.Tensor:
-    """A cached page-locked staging buffer of at least nbytes (grown geometrically, one per process)."""
-    buf = _PINNED.get("buf")
+    """Page-locked staging memory of at least nbytes from a ring of 4 cached buffers (grown geometrically): results
+    exported through it stay valid until the fourth following export."""
+    i = _PINNED["next"]
+    _PINNED["next"] = (i + 1) % len(_PINNED["ring"])
+    buf = _PINNED["ring"][i]
     if buf is None or buf.numel() < nbytes:
         buf = torch.empty(max(nbytes, 2 * (buf.numel() if buf is not None else 0), 1 << 20), dtype=torch.uint8,
                           pin_memory=True)
-        _PINNED["buf"] = buf
+        _PINNED["ring"][i] = buf
     return buf
 
 
 def csr_from_matrix(P: torch.Tensor, counts: torch.Tensor | None = None):
     """Ascending non-zero columns per row -> (rowptr int64 numpy, colidx int32 numpy).
     Matrices up to 16 MB (M <= 2048) are compacted into a full-capacity index buffer and brought to the host with
-    ONE asynchronous copy into page-locked memory and one sync (a pageable `.cpu()` of the 3 MB list plus the
-    `.item()` needed to size it cost 1.5 ms at C2, more than the whole device pass); larger ones size the list first."""
+    ONE asynchronous copy into page-locked memory and one sync; the arrays returned are VIEWS of that page-locked
+    buffer (valid until the fourth following export — copy them to keep them longer).  Round 1 sized the list with an
+    `.item()`, copied it with a pageable `.cpu()` and again into numpy: 1.5 ms at C2, more than the whole device
+    pass; a fresh 3 MB numpy copy alone costs 1 ms (page faults).  Larger matrices size the list first."""
     rows, cols = P.shape
     dev = P.device
     if counts is None:
@@ -377,9 +382,8 @@ def csr_from_matrix(P: torch.Tensor, counts: torch.Tensor | None = None):
         host = _pinned(both.numel())[:both.numel()]
         host.copy_(both, non_blocking=True)
         torch.cuda.current_stream(dev).synchronize()
-        rp = host[:head].view(torch.int64).numpy().copy()
-        total = int(rp[-1])
-        return rp, host[head:head + total * 4].view(torch.int32).numpy().copy()
+        rp = host[:head].view(torch.int64).numpy()
+        return rp, host[head:head + int(rp[-1]) * 4].view(torch.int32).numpy()
     rowptr = torch.zeros(rows + 1, dtype=torch.int64, device=dev)
     torch.cumsum(counts, 0, out=rowptr[1:])
     total = int(rowptr[-1].item())
@@ -390,7 +394,7 @@ def csr_from_matrix(P: torch.Tensor, counts: torch.Tensor | None = None):
     host[:head].copy_(rowptr.view(torch.uint8), non_blocking=True)
     host[head:head + total * 4].copy_(colidx[:total].view(torch.uint8), non_blocking=True)
     torch.cuda.current_stream(dev).synchronize()
-    return host[:head].view(torch.int64).numpy().copy(), host[head:head + total * 4].view(torch.int32).numpy().copy()
+    return host[:head].view(torch.int64).numpy(), host[head:head + total * 4].view(torch.int32).numpy()
 
 
 class SurvivorRows:
