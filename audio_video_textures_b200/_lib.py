@@ -34,6 +34,8 @@ SIGNATURES = {
                               _p, _i64, _p, _i64, _f32, _p, _p, _int, _p],
     "avtex_diag_filter_pow_sym": [_p, _i64, _i64, C.POINTER(_f32), _int, _int, _i64, _p, _i64, _p, _i64, _f32, _p, _p,
                                   _int, _p],
+    "avtex_diag_filter_pow_res": [_p, _i64, _i64, _i64, _i64, C.POINTER(_f32), _int, _int, _i64, _i64, _i64, _p, _i64, _p,
+                                  _i64, _f32, _p, _p, _int, _int, _p],
     "avtex_future_cost_sweep": [_p, _i64, _i64, _i64, _i64, _p, _p, _f32, _p, _p, _int, _p],
     "avtex_future_cost_fused": [_p, _i64, _i64, _f32, _f32, _int, _p, _i64, _p, _p, _p, _int, _p],
     "avtex_pow_matrix": [_p, _i64, _i64, _i64, _f32, _p, _i64, _int, _p],
@@ -65,7 +67,8 @@ class GramJob(C.Structure):
     _fields_ = [("row0", _i64), ("rows", _i64), ("col0", _i64), ("cols", _i64),
                 ("D", _p), ("d_row0", _i64), ("ldd", _i64),
                 ("DT", _p), ("dt_row0", _i64), ("ldt", _i64),
-                ("symmetric", _int), ("count_stats", _int)]
+                ("symmetric", _int), ("count_stats", _int),
+                ("k_off", _i64), ("sq_off", _i64), ("sq_stride", _i64)]
 
 
 SIGNATURES["avtex_future_cost_fused_peer"] = [_p, _i64, _i64, _i64, _i64, _f32, _f32, _int, _int, _int,

@@ -111,9 +111,10 @@ def main(args, video_name: str):
     if args.feats != "RGB":
         raise NotImplementedError("only -f RGB is on the hot path")
     frames = input_frames if input_frames.is_cuda else input_frames.cuda(non_blocking=True)
-    D1, used = engine.pairwise_l2(frames if frames.dtype in (torch.uint8, torch.float32) else frames.float())
     stride = 1 if args.model_type in (1, 2) else args.stride            # video_textures.py:276-283
-    D2, D3 = engine.diag_filter(D1, args.filter_size, stride, p=0.7)
+    # only P3_new is consumed below, so D1 itself need not exist: with -stride s the filter reads D1[i,j] only where
+    # i = j (mod s), and engine.distance_filter computes just those residue-class blocks (1/s of the pairs; same bits)
+    D2, D3, used = engine.distance_filter(frames, args.filter_size, stride, p=0.7)
     fc = engine.future_cost_fused(D3, 0.997, verbose=True)
     stats = engine.new_stats(D3.device)
     D3_new = engine.future_cost_finalize(D3, fc.mvec, 0.997, stats=stats)

@@ -43,9 +43,11 @@ __device__ __noinline__ float pow_pos_call(float x, float p) { return pow_pos(x,
 // b - a = b0 - a_base, so ownership is per thread; CTAs entirely below the diagonal exit at once) and the strictly
 // upper ones are mirrored through a shared-memory tile so that the mirrored rows are written as 64-byte runs:
 // half the loads, FMAs and pows (stride 1 is FP32-pipe bound) and half the D1 bytes (stride 4 is HBM bound).
-template <int FS, int S, int FR, bool PACKED, bool SYM>
+// RES: D1 is given as S residue-class matrices (avtex_diag_filter_pow_res): input element (g, h) with g = h (mod S) lives
+// in plane g % S at [g / S, h / S]; the walk along a diagonal visits the planes round-robin, in the same tap order.
+template <int FS, int S, int FR, bool PACKED, bool SYM, bool RES>
 __global__ void __launch_bounds__(FT)
-diag_filter_kernel(const float *__restrict__ D1, int64_t ld1, int64_t in_row0, int64_t in_rows, const Taps64 taps,
+diag_filter_kernel(const float *__restrict__ D1, int64_t ld1, int64_t plane, int64_t in_row0, int64_t in_rows, const Taps64 taps,
                    const TapPairs pairs, int64_t a0, int64_t rows_out, int64_t m, float *__restrict__ D2, int64_t ld2,
                    float *__restrict__ D3, int64_t ld3, float p, double *sum, unsigned long long *nnz) {
     __shared__ double sred[32];
@@ -81,15 +83,18 @@ diag_filter_kernel(const float *__restrict__ D1, int64_t ld1, int64_t in_row0, i
     const bool mirror = SYM && b0 > a_base;                                 // ... b > a: also stored as D2[b, a]
     const int64_t grow = a_base * S;                                        // global input row at t = 0
     const int64_t gcol = b0 * S;
-    const float *src = D1 + (grow - in_row0) * ld1 + gcol;
+    const float *src = RES ? D1 + (a_base - in_row0) * ld1 + b0 : D1 + (grow - in_row0) * ld1 + gcol;   // RES: class rows
     const int64_t step = ld1 + 1;
+    const int64_t in_end = RES ? (in_row0 + in_rows) * S : in_row0 + in_rows;   // one past the last (global) input row held
+    // address of the input element at diagonal step t
+    auto at = [&](int t) -> const float * { return RES ? src + (t % S) * plane + (t / S) * step : src + t * step; };
     float acc[FR];
 #pragma unroll
     for (int i = 0; i < FR; ++i) acc[i] = 0.f;
     // CTA-uniform: every load of every thread is in range -> no per-load predicates (all CTAs except
     // those on the matrix border)
     const bool interior = (b_blk * S >= 0) && ((b_blk + FT - 1) * S + T - 1 < n_in) &&
-                          (grow + T - 1 < in_row0 + in_rows) && (grow + T - 1 < n_in);
+                          (grow + T - 1 < in_end) && (grow + T - 1 < n_in);
     if (!owner) {
         // nothing to compute: the mirror image of these outputs is owned by another CTA
     } else if (interior && PACKED) {
@@ -101,8 +106,7 @@ diag_filter_kernel(const float *__restrict__ D1, int64_t ld1, int64_t in_row0, i
         for (int p2 = 0; p2 < FR / 2; ++p2) acc2[p2] = make_float2(0.f, 0.f);
 #pragma unroll
         for (int t = 0; t < T; ++t) {
-            const float x = __ldg(src);
-            src += step;
+            const float x = __ldg(at(t));
             const float2 x2 = make_float2(x, x);
 #pragma unroll
             for (int p2 = 0; p2 < FR / 2; ++p2) {
@@ -115,8 +119,7 @@ diag_filter_kernel(const float *__restrict__ D1, int64_t ld1, int64_t in_row0, i
     } else if (interior) {
 #pragma unroll
         for (int t = 0; t < T; ++t) {
-            const float x = __ldg(src);
-            src += step;
+            const float x = __ldg(at(t));
 #pragma unroll
             for (int i = 0; i < FR; ++i) {
                 const int kk = t - i * S;
@@ -126,9 +129,8 @@ diag_filter_kernel(const float *__restrict__ D1, int64_t ld1, int64_t in_row0, i
     } else {
 #pragma unroll
         for (int t = 0; t < T; ++t) {
-            const bool ok = (gcol + t >= 0) && (gcol + t < n_in) && (grow + t < in_row0 + in_rows);
-            const float x = ok ? __ldg(src) : 0.f;
-            src += step;
+            const bool ok = (gcol + t >= 0) && (gcol + t < n_in) && (grow + t < in_end);
+            const float x = ok ? __ldg(at(t)) : 0.f;
 #pragma unroll
             for (int i = 0; i < FR; ++i) {
                 const int kk = t - i * S;
@@ -256,7 +258,7 @@ diag_filter_generic_kernel(const float *__restrict__ D1, int64_t ld1, int64_t in
 template <int S> constexpr int filter_r() { return S == 1 ? 16 : 8; }
 
 template <int FS, int S, int FR = filter_r<S>()>
-void launch_fast(const float *D1, int64_t ld1, int64_t in_row0, int64_t in_rows, const float *h_w, int64_t a0,
+void launch_fast(const float *D1, int64_t ld1, int64_t plane, int64_t in_row0, int64_t in_rows, const float *h_w, int64_t a0,
                  int64_t rows_out, int64_t m, float *D2, int64_t ld2, float *D3, int64_t ld3, float p,
                  double *sum, unsigned long long *nnz, bool symmetric, cudaStream_t st) {
     Taps64 taps;
@@ -266,8 +268,14 @@ void launch_fast(const float *D1, int64_t ld1, int64_t in_row0, int64_t in_rows,
     dim3 grid((unsigned)((m + FR - 1 + FT - 1) / FT), (unsigned)((rows_out + FR - 1) / FR));
     static const bool packed_off = []() { const char *e = getenv("AVTEX_FILTER_FFMA2"); return e != nullptr && e[0] == '0'; }();
 #define AVTEX_FILTER_LAUNCH(PACKED_, SYM_)                                                                         \
-    diag_filter_kernel<FS, S, FR, PACKED_, SYM_><<<grid, FT, 0, st>>>(D1, ld1, in_row0, in_rows, taps, pairs, a0, rows_out, m, \
-                                                                    D2, ld2, D3, ld3, p, sum, nnz)
+    do {                                                                                                            \
+        if (plane != 0)                                                                                             \
+            diag_filter_kernel<FS, S, FR, PACKED_, SYM_, (S > 1)><<<grid, FT, 0, st>>>(                             \
+                D1, ld1, plane, in_row0, in_rows, taps, pairs, a0, rows_out, m, D2, ld2, D3, ld3, p, sum, nnz);     \
+        else                                                                                                        \
+            diag_filter_kernel<FS, S, FR, PACKED_, SYM_, false><<<grid, FT, 0, st>>>(                               \
+                D1, ld1, 0, in_row0, in_rows, taps, pairs, a0, rows_out, m, D2, ld2, D3, ld3, p, sum, nnz);         \
+    } while (0)
     const bool packed = (S == 1) && !packed_off;
     if (symmetric) {                                                 // folded triangle (see the kernel)
         static_assert(FT % FR == 0, "the symmetric grid needs FT to be a multiple of FR");
@@ -319,7 +327,8 @@ extern "C" int avtex_pow_matrix(const float *D, int64_t ld, int64_t rows, int64_
 
 namespace {
 
-int diag_filter_impl(const float *D1, int64_t ld1, int64_t in_row0, int64_t in_rows, const float *h_w, int fs, int stride,
+int diag_filter_impl(const float *D1, int64_t ld1, int64_t plane, int64_t in_row0, int64_t in_rows, const float *h_w, int fs,
+                     int stride,
                      int64_t a0, int64_t rows_out, int64_t m, float *D2, int64_t ld2, float *D3, int64_t ld3, float p,
                      double *sum, unsigned long long *nnz, bool symmetric, int device, void *stream) {
     AVTEX_ENTER(device);
@@ -327,11 +336,20 @@ int diag_filter_impl(const float *D1, int64_t ld1, int64_t in_row0, int64_t in_r
     AVTEX_REQUIRE(m >= 1 && rows_out >= 1 && a0 >= 0 && a0 + rows_out <= m && ld2 >= m,
                   "diag_filter: bad output shape a0=%lld rows=%lld m=%lld", (long long)a0,
                   (long long)rows_out, (long long)m);
-    AVTEX_REQUIRE(ld1 >= (m - 1) * stride + fs, "diag_filter: ld1=%lld too small", (long long)ld1);
-    AVTEX_REQUIRE(in_row0 >= 0 && in_row0 <= a0 * stride &&
-                      in_row0 + in_rows >= (a0 + rows_out - 1) * stride + fs,
-                  "diag_filter: D1 rows [%lld, %lld) do not cover the rows needed", (long long)in_row0,
-                  (long long)(in_row0 + in_rows));
+    if (plane != 0) {                                                // residue-class planes; in_row0 / in_rows in CLASS rows
+        const int64_t need_cols = ((m - 1) * stride + fs + stride - 1) / stride;     // columns of every class matrix
+        const int64_t last_row = a0 + rows_out - 1 + (fs - 1) / stride;              // last class row read
+        AVTEX_REQUIRE(stride >= 2 && in_row0 >= 0 && in_row0 <= a0 && in_row0 + in_rows > last_row &&
+                          ld1 >= need_cols && plane >= in_rows * ld1,
+                      "diag_filter (residue form): needs stride >= 2 and class rows [%lld, %lld] x %lld columns",
+                      (long long)a0, (long long)last_row, (long long)need_cols);
+    } else {
+        AVTEX_REQUIRE(ld1 >= (m - 1) * stride + fs, "diag_filter: ld1=%lld too small", (long long)ld1);
+        AVTEX_REQUIRE(in_row0 >= 0 && in_row0 <= a0 * stride &&
+                          in_row0 + in_rows >= (a0 + rows_out - 1) * stride + fs,
+                      "diag_filter: D1 rows [%lld, %lld) do not cover the rows needed", (long long)in_row0,
+                      (long long)(in_row0 + in_rows));
+    }
     AVTEX_REQUIRE((sum == nullptr) == (nnz == nullptr), "diag_filter: sum and nnz go together");
     AVTEX_REQUIRE(D3 == nullptr || ld3 >= m, "diag_filter: ld3 too small");
     AVTEX_REQUIRE(!symmetric || (a0 == 0 && rows_out == m && in_row0 == 0),
@@ -341,7 +359,7 @@ int diag_filter_impl(const float *D1, int64_t ld1, int64_t in_row0, int64_t in_r
 #define AVTEX_FAST(FS_, S_)                                                                            \
     case FS_ * 100 + S_:                                                                               \
         AVTEX_REQUIRE((rows_out + filter_r<S_>() - 1) / filter_r<S_>() <= 65535, "diag_filter: too many row bands"); \
-        launch_fast<FS_, S_>(D1, ld1, in_row0, in_rows, h_w, a0, rows_out, m, D2, ld2, D3, ld3, p, sum, nnz, symmetric, st); \
+        launch_fast<FS_, S_>(D1, ld1, plane, in_row0, in_rows, h_w, a0, rows_out, m, D2, ld2, D3, ld3, p, sum, nnz, symmetric, st); \
         break;
     switch (key) {
         AVTEX_FAST(40, 1)
@@ -350,6 +368,8 @@ int diag_filter_impl(const float *D1, int64_t ld1, int64_t in_row0, int64_t in_r
         AVTEX_FAST(16, 4)
         AVTEX_FAST(8, 1)
         default: {                                                   // any (fs, stride): no symmetric shortcut
+            AVTEX_REQUIRE(plane == 0, "diag_filter (residue form): no register-resident kernel for fs=%d stride=%d", fs,
+                          stride);
             TapsBig taps;
             for (int i = 0; i < 960; ++i) taps.w[i] = (i < fs) ? h_w[i] : 0.f;
             for (int64_t r = 0; r < rows_out; r += 65535) {          // gridDim.y <= 65535: row bands of that many rows
@@ -372,13 +392,22 @@ extern "C" int avtex_diag_filter_pow(const float *D1, int64_t ld1, int64_t in_ro
                                      int fs, int stride, int64_t a0, int64_t rows_out, int64_t m,
                                      float *D2, int64_t ld2, float *D3, int64_t ld3, float p,
                                      double *sum, unsigned long long *nnz, int device, void *stream) {
-    return diag_filter_impl(D1, ld1, in_row0, in_rows, h_w, fs, stride, a0, rows_out, m, D2, ld2, D3, ld3, p, sum, nnz,
+    return diag_filter_impl(D1, ld1, 0, in_row0, in_rows, h_w, fs, stride, a0, rows_out, m, D2, ld2, D3, ld3, p, sum, nnz,
                             false, device, stream);
 }
 
 extern "C" int avtex_diag_filter_pow_sym(const float *D1, int64_t ld1, int64_t n_rows, const float *h_w, int fs, int stride,
                                          int64_t m, float *D2, int64_t ld2, float *D3, int64_t ld3, float p,
                                          double *sum, unsigned long long *nnz, int device, void *stream) {
-    return diag_filter_impl(D1, ld1, 0, n_rows, h_w, fs, stride, 0, m, m, D2, ld2, D3, ld3, p, sum, nnz, true, device,
+    return diag_filter_impl(D1, ld1, 0, 0, n_rows, h_w, fs, stride, 0, m, m, D2, ld2, D3, ld3, p, sum, nnz, true, device,
                             stream);
+}
+
+extern "C" int avtex_diag_filter_pow_res(const float *D1r, int64_t ld1, int64_t plane, int64_t in_row0, int64_t in_rows,
+                                         const float *h_w, int fs, int stride, int64_t a0, int64_t rows_out, int64_t m,
+                                         float *D2, int64_t ld2, float *D3, int64_t ld3, float p, double *sum,
+                                         unsigned long long *nnz, int symmetric, int device, void *stream) {
+    AVTEX_REQUIRE(plane > 0, "diag_filter (residue form): plane stride must be positive");
+    return diag_filter_impl(D1r, ld1, plane, in_row0, in_rows, h_w, fs, stride, a0, rows_out, m, D2, ld2, D3, ld3, p, sum,
+                            nnz, symmetric != 0, device, stream);
 }

@@ -68,9 +68,10 @@ struct GramJob {
     int64_t d_row0, ldd;
     float *DT;
     int64_t dt_row0, ldt;
-    int symmetric, count_stats, TM, TN, tile_begin, pad_;
+    int symmetric, count_stats, TM, TN, tile_begin, k_off;   // k_off: first operand byte column of this job's K range
+    int64_t sq_off, sq_stride;                              // norm of job row a = sqnorm[sq_off + a * sq_stride]
 };
-constexpr int MAX_JOBS = 16;
+constexpr int MAX_JOBS = 32;      // 8 ranks x 4 residue classes; GramArgs stays below the 32 KB launch-parameter limit (CUDA >= 12.1)
 
 struct GramArgs {
     int64_t n, kp;
@@ -199,7 +200,7 @@ __device__ __forceinline__ void epilogue_tile(const GramArgs &args, const GramJo
     const int64_t row_end = job.row0 + job.rows, col_end = job.col0 + job.cols;
     const int64_t r = r0 + lane;
     const bool r_ok = r < row_end;
-    const uint32_t nr = r_ok ? (uint32_t)__ldg(args.sqnorm + r) : 0u;
+    const uint32_t nr = r_ok ? (uint32_t)__ldg(args.sqnorm + job.sq_off + r * job.sq_stride) : 0u;
     int64_t rows_here = row_end - r0;                              // valid rows of this warp's 32
     if (rows_here > 32) rows_here = 32;
     const bool sym = job.symmetric != 0;
@@ -219,7 +220,8 @@ __device__ __forceinline__ void epilogue_tile(const GramArgs &args, const GramJo
         const int64_t cbase = c0 + cc * 32;
         if (cbase >= col_end || rows_here <= 0) continue;
         if (sym && cbase + 31 < r0) continue;                     // whole chunk below the diagonal for this warp
-        const uint32_t nc_lane = (cbase + lane < col_end) ? (uint32_t)__ldg(args.sqnorm + cbase + lane) : 0u;
+        const uint32_t nc_lane = (cbase + lane < col_end)
+                                     ? (uint32_t)__ldg(args.sqnorm + job.sq_off + (cbase + lane) * job.sq_stride) : 0u;
         // warp-uniform: all 32 x 32 elements are valid and (symmetric) strictly above the diagonal ->
         // no per-element predicates (the per-element branches of the general path were the critical path
         // of the whole kernel at K = 12288: the epilogue, not the MMAs, set the tile time)
@@ -402,8 +404,8 @@ gram_l2_s8_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                     mbar_wait(empty_bar + 8 * stage, phase ^ 1);
                     const uint32_t sa = tiles + stage * STAGE_BYTES, sb = sa + A_BYTES;
                     mbar_arrive_expect_tx(full_bar + 8 * stage, STAGE_BYTES);
-                    tma_load_2d(sa, &map_a, full_bar + 8 * stage, kb * BKB, row_a);
-                    tma_load_2d(sb, &map_b, full_bar + 8 * stage, kb * BKB, row_b);
+                    tma_load_2d(sa, &map_a, full_bar + 8 * stage, job.k_off + kb * BKB, row_a);
+                    tma_load_2d(sb, &map_b, full_bar + 8 * stage, job.k_off + kb * BKB, row_b);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
@@ -667,10 +669,11 @@ gram_l2_s8_2cta_kernel(const __grid_constant__ CUtensorMap map, const GramArgs a
                     const uint32_t sa = tiles + stage * STAGE2_BYTES, sb = sa + A_BYTES;
                     if (leader) mbar_arrive_expect_tx(full_bar + 8 * stage, 2 * STAGE2_BYTES);
                     else mbar_arrive_cluster(full_bar + 8 * stage, 0);
-                    if (args.l2_hint >= 1) tma_load_2d_2sm_hint(sa, &map, full_bar + 8 * stage, kb * BKB, row_a, pol_last);
-                    else tma_load_2d_2sm(sa, &map, full_bar + 8 * stage, kb * BKB, row_a);
-                    if (args.l2_hint >= 2) tma_load_2d_2sm_hint(sb, &map, full_bar + 8 * stage, kb * BKB, row_b, pol_last);
-                    else tma_load_2d_2sm(sb, &map, full_bar + 8 * stage, kb * BKB, row_b);
+                    const int kc = job.k_off + kb * BKB;
+                    if (args.l2_hint >= 1) tma_load_2d_2sm_hint(sa, &map, full_bar + 8 * stage, kc, row_a, pol_last);
+                    else tma_load_2d_2sm(sa, &map, full_bar + 8 * stage, kc, row_a);
+                    if (args.l2_hint >= 2) tma_load_2d_2sm_hint(sb, &map, full_bar + 8 * stage, kc, row_b, pol_last);
+                    else tma_load_2d_2sm(sb, &map, full_bar + 8 * stage, kc, row_b);
                     if (++stage == STAGES2) { stage = 0; phase ^= 1; }
                 }
             }
@@ -805,6 +808,7 @@ int launch_gram_jobs(const void *operand, bool is_signed, int64_t n, int64_t k_e
     if (const char *e = getenv("AVTEX_GRAM_HINT")) a.l2_hint = atoi(e);
     if (const char *e = getenv("AVTEX_GRAM_ST")) st_mode = atoi(e);
     int total = 0;
+    int64_t map_k = k_extent;                                       // columns the tensor map must expose
     for (int j = 0; j < num_jobs; ++j) {
         const AvtexGramJob &in = jobs[j];
         AVTEX_REQUIRE(in.rows >= 1 && in.cols >= 1 && in.row0 >= 0 && in.col0 >= 0 && in.row0 + in.rows <= n &&
@@ -827,7 +831,14 @@ int launch_gram_jobs(const void *operand, bool is_signed, int64_t n, int64_t k_e
         o.TM = int((in.rows + bm - 1) / bm);
         o.TN = int((in.cols + BN - 1) / BN);
         o.tile_begin = total;
-        o.pad_ = 0;
+        AVTEX_REQUIRE(in.k_off >= 0 && in.k_off + k_extent <= pitch && (in.k_off == 0 || k_extent % BKB == 0) &&
+                          in.sq_off >= 0 && in.sq_stride >= 0,
+                      "gram_l2: job %d residue fields (k_off %lld needs K %% 128 == 0 and k_off + K <= ld)", j,
+                      (long long)in.k_off);
+        o.k_off = (int)in.k_off;
+        o.sq_off = in.sq_off;
+        o.sq_stride = in.sq_stride > 0 ? in.sq_stride : 1;
+        if (in.k_off + k_extent > map_k) map_k = in.k_off + k_extent;
         total += two_cta ? count_tiles2(o.TM, o.TN, o.symmetric, a.group_m) : count_tiles(o.TM, o.TN, o.symmetric);
     }
     a.num_tiles = total;
@@ -836,7 +847,7 @@ int launch_gram_jobs(const void *operand, bool is_signed, int64_t n, int64_t k_e
     if (int rc = get_encode_fn(&enc)) return rc;
     if (two_cta) {
         CUtensorMap map;
-        if (int rc = make_map(enc, &map, operand, n, k_extent, pitch, BM)) return rc;
+        if (int rc = make_map(enc, &map, operand, n, map_k, pitch, BM)) return rc;
         // cudaFuncSetAttribute is idempotent: the atomic flag only skips repeats, two racing host threads both succeed
         static std::atomic<bool> attr2_set[64];
         if (device >= 64 || !attr2_set[device].load(std::memory_order_acquire)) {
@@ -852,8 +863,8 @@ int launch_gram_jobs(const void *operand, bool is_signed, int64_t n, int64_t k_e
         return 0;
     }
     CUtensorMap map_a, map_b;
-    if (int rc = make_map(enc, &map_a, operand, n, k_extent, pitch, BM)) return rc;
-    if (int rc = make_map(enc, &map_b, operand, n, k_extent, pitch, BN)) return rc;
+    if (int rc = make_map(enc, &map_a, operand, n, map_k, pitch, BM)) return rc;
+    if (int rc = make_map(enc, &map_b, operand, n, map_k, pitch, BN)) return rc;
     static std::atomic<bool> attr_set[64];
     if (device >= 64 || !attr_set[device].load(std::memory_order_acquire)) {
         AVTEX_CUDA(cudaFuncSetAttribute(gram_l2_s8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
@@ -878,6 +889,7 @@ int launch_gram(const void *operand, bool is_signed, int64_t n, int64_t k_extent
     job.DT = symmetric ? D : nullptr; job.dt_row0 = 0; job.ldt = ldd;
     job.symmetric = symmetric ? 1 : 0;
     job.count_stats = 1;
+    job.k_off = 0; job.sq_off = 0; job.sq_stride = 1;
     return launch_gram_jobs(operand, is_signed, n, k_extent, pitch, sqnorm, &job, 1, sum, nnz, nullptr, device, stream);
 }
 

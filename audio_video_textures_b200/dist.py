@@ -211,12 +211,28 @@ class PeerBuffers:
     (`SymmetricShardWorkspace`) and plain local buffers shared by virtual ranks (`VirtualBox`)."""
     MAX_SWEEPS = 2046
 
-    def __init__(self, n, filter_size, stride, rank, world, device):
+    def __init__(self, n, filter_size, stride, rank, world, device, residues: bool = False):
         self.n, self.fs, self.stride, self.rank, self.world, self.device = n, filter_size, stride, rank, world, device
         self.plans = [plan_shards(n, filter_size, stride, world, r) for r in range(world)]
         self.plan = self.plans[rank]
-        self.ld = (n + 31) // 32 * 32
-        self.rows_max = max(p.r_hi - p.r_lo for p in self.plans)
+        # residues: the shards hold the `stride` residue-class planes (engine.gram_l2_residues) instead of D1 rows.  In
+        # class coordinates the pipeline is a stride-1 filter of fs/stride taps per plane over N/stride frames, so
+        # the SAME planner describes it (cplans: class rows owned / computed / haloed by every rank) and the output
+        # row ranges (a0, a1, a1h) coincide with the full plan's.
+        self.residues = bool(residues)
+        if self.residues:
+            if (filter_size, stride) not in engine.RESIDUE_FAST or n % stride or filter_size % stride:
+                raise ValueError(f"residue-class shards need (fs, stride) in {sorted(engine.RESIDUE_FAST)} and "
+                                 f"N % stride == 0 (got fs={filter_size}, stride={stride}, N={n})")
+            self.cplans = [plan_shards(n // stride, filter_size // stride, 1, world, r) for r in range(world)]
+            assert all((c.m, c.a0, c.a1, c.a1h) == (p.m, p.a0, p.a1, p.a1h) for c, p in zip(self.cplans, self.plans))
+            self.ld = (n // stride + 31) // 32 * 32
+            self.rows_c = max(c.r_hi - c.r_lo for c in self.cplans)           # class rows per plane and rank
+            self.rows_max = stride * self.rows_c                              # the buffer stacks the planes
+        else:
+            self.cplans = None
+            self.ld = (n + 31) // 32 * 32
+            self.rows_max = max(p.r_hi - p.r_lo for p in self.plans)
         self.m = self.plan.m
         self.mpad = (self.m + 31) // 32 * 32
         self.npad = (n + 31) // 32 * 32
@@ -251,6 +267,14 @@ class PeerBuffers:
         p = self.plan
         return self.d1[:p.r_hi - p.r_lo, :self.n]
 
+    def planes(self) -> torch.Tensor:
+        """residues: this rank's class planes [stride, class rows held, ld] (plane stride = rows_c * ld)."""
+        c = self.cplans[self.rank]
+        return self.d1.view(self.stride, self.rows_c, self.ld)[:, :c.r_hi - c.r_lo]
+
+    def peer_plane_rows(self, r: int, plane: int, row_off: int, rows: int) -> torch.Tensor:
+        return self.peer_d1_rows(r, plane * self.rows_c + row_off, rows)
+
 
 class SymmetricShardWorkspace(PeerBuffers):
     """Shards in torch symmetric memory (peer-mapped over NVLink / NVSwitch).
@@ -262,9 +286,10 @@ class SymmetricShardWorkspace(PeerBuffers):
     stores from the epilogue), so every rank does N^2/(2G) pairs and no separate exchange step exists.
     """
 
-    def __init__(self, n: int, filter_size: int, stride: int, rank: int, world: int, device, group=None):
+    def __init__(self, n: int, filter_size: int, stride: int, rank: int, world: int, device, group=None,
+                 residues: bool = False):
         import torch.distributed._symmetric_memory as symm_mem
-        super().__init__(n, filter_size, stride, rank, world, device)
+        super().__init__(n, filter_size, stride, rank, world, device, residues)
         group = dist.group.WORLD if group is None else group
         self.group = group
         self.d1 = symm_mem.empty((self.rows_max, self.ld), dtype=torch.float32, device=device)
@@ -341,10 +366,31 @@ class RankStep:
     # -- K1: my tiles, transposes pushed into the peers' shards
     def gram(self):
         pb = self.pb
-        engine.gram_l2_jobs(self.pf, symmetric_jobs(pb.plans, pb.rank, pb.d1_ptrs, pb.ld, pb.stride))
+        if not pb.residues:
+            engine.gram_l2_jobs(self.pf, symmetric_jobs(pb.plans, pb.rank, pb.d1_ptrs, pb.ld, pb.stride))
+            return
+        # one job list per residue-class plane (the same symmetric split, in class rows), all in ONE launch
+        n, k = self.x.shape
+        if k % 128 or self.x.stride(0) != k:
+            raise engine._lib.AvtexError("residue-class shards need dense rows with K % 128 == 0")
+        plane_bytes = pb.rows_c * pb.ld * 4
+        jobs = []
+        for r in range(pb.stride):
+            for j in symmetric_jobs(pb.cplans, pb.rank, [b + r * plane_bytes for b in pb.d1_ptrs], pb.ld, 1):
+                jobs.append(dict(j, k_off=r * k, sq_off=r, sq_stride=pb.stride))
+        engine.gram_l2_jobs(self.pf, jobs, n=n // pb.stride, ld=pb.stride * k)
 
     def halo(self):
         pb = self.pb
+        if pb.residues:
+            c = pb.cplans[pb.rank]
+            mine = pb.d1.view(pb.stride, pb.rows_c, pb.ld)
+            for owner, row, rows in halo_sources(pb.cplans, pb.rank, 1):
+                for r in range(pb.stride):
+                    src = pb.peer_plane_rows(owner, r, row - pb.cplans[owner].r_lo, rows)
+                    mine[r, row - c.r_lo: row - c.r_lo + rows].copy_(src)
+            self.D1 = pb.planes()
+            return
         p = pb.plan
         for owner, row, rows in halo_sources(pb.plans, pb.rank, pb.stride):
             src = pb.peer_d1_rows(owner, row - pb.plans[owner].r_lo, rows)
@@ -355,6 +401,11 @@ class RankStep:
     def filter(self):
         pb = self.pb
         p = pb.plan
+        if pb.residues:
+            self.D2, self.D3 = engine.diag_filter_residues(self.D1, pb.n, pb.fs, pb.stride, p=self.p, a0=p.a0,
+                                                           rows_out=p.a1h - p.a0, in_row0=pb.cplans[pb.rank].r_lo,
+                                                           symmetric=False)
+            return
         self.D2, self.D3 = engine.diag_filter(self.D1, pb.fs, pb.stride, p=self.p, m=p.m, a0=p.a0,
                                               rows_out=p.a1h - p.a0, in_row0=p.r_lo)
 
@@ -590,7 +641,7 @@ def gather_survivors(res: ShardResult, group=None):
 # --------------------------------------------------------------------------- virtual ranks on one device
 class _VirtualRankBuffers(PeerBuffers):
     def __init__(self, box: "VirtualBox", rank: int):
-        super().__init__(box.n, box.fs, box.stride, rank, box.world, box.device)
+        super().__init__(box.n, box.fs, box.stride, rank, box.world, box.device, box.residues)
         self.box = box
 
     def barrier(self, channel: int):
@@ -607,8 +658,9 @@ class VirtualBox:
     co-resident on G streams — the same flag barrier as on a real 8-GPU box, so tests/test_gpu_virtual.py
     checks the G = 2 / 4 / 8 paths bit-for-bit against the single-GPU pipeline on a 1-GPU machine."""
 
-    def __init__(self, n: int, filter_size: int, stride: int, world: int, device):
+    def __init__(self, n: int, filter_size: int, stride: int, world: int, device, residues: bool = False):
         self.n, self.fs, self.stride, self.world, self.device = n, filter_size, stride, world, device
+        self.residues = residues
         self.ranks = [_VirtualRankBuffers(self, r) for r in range(world)]
         for pb in self.ranks:
             pb.d1 = torch.empty((pb.rows_max, pb.ld), dtype=torch.float32, device=device)

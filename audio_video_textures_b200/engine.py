@@ -192,7 +192,7 @@ def gram_l2(pf: PackedFrames, row0: int = 0, rows: int | None = None, symmetric:
 
 
 def gram_l2_jobs(pf: PackedFrames, jobs: list, stats: torch.Tensor | None = None, device=None,
-                 clock_probe: torch.Tensor | None = None):
+                 clock_probe: torch.Tensor | None = None, n: int | None = None, ld: int | None = None):
     """K1, general form: `jobs` is a list of dicts with the fields of AvtexGramJob (D / DT are raw device
     pointers, possibly into a peer GPU's symmetric-memory buffer).  `clock_probe`: int64[2] on the device,
     receives (SM cycles, nanoseconds) of CTA 0's tile loop (bench.py's in-kernel clock measurement)."""
@@ -202,10 +202,12 @@ def gram_l2_jobs(pf: PackedFrames, jobs: list, stats: torch.Tensor | None = None
         dst.D, dst.d_row0, dst.ldd = j.get("D"), j.get("d_row0", 0), j.get("ldd", 0)
         dst.DT, dst.dt_row0, dst.ldt = j.get("DT"), j.get("dt_row0", 0), j.get("ldt", 0)
         dst.symmetric, dst.count_stats = int(j.get("symmetric", 0)), int(j.get("count_stats", 0))
-    n = pf.packed.shape[0]
+        dst.k_off, dst.sq_off, dst.sq_stride = j.get("k_off", 0), j.get("sq_off", 0), j.get("sq_stride", 1)
+    n = pf.packed.shape[0] if n is None else n             # n / ld overridden by the residue-class view [N/s, s*K]
     s, z = _stats_ptrs(stats)
     k_extent = pf.packed.shape[1] if pf.signed else pf.k
-    _lib.call("avtex_gram_l2_jobs", _lib.ptr(pf.packed), 1 if pf.signed else 0, n, k_extent, pf.packed.stride(0),
+    _lib.call("avtex_gram_l2_jobs", _lib.ptr(pf.packed), 1 if pf.signed else 0, n, k_extent,
+              pf.packed.stride(0) if ld is None else ld,
               _lib.ptr(pf.sqnorm), arr, len(jobs), s, z, _lib.ptr(clock_probe), _dev(pf.packed), _stream(pf.packed))
 
 
@@ -499,6 +501,80 @@ def diag_filter(D1: torch.Tensor, filter_size: int, stride: int = 1, p: float | 
                   a0, rows_out, m, _lib.ptr(D2), D2.stride(0), _lib.ptr(D3), D3.stride(0) if D3 is not None else 0,
                   pf, s, z, _dev(D1), _stream(D1))
     return D2, D3
+
+
+# --------------------------------------------------------------------------- stride-s pipelines: residue classes
+# A stride-s filter reads D1[i, j] only where i = j (mod s):  D2[a,b] = sum_k w[k] D1[s*a + k, s*b + k].  Those
+# entries are exactly the s Gram matrices of the frames of one residue class each (N/s x N/s), i.e. 1/s of the
+# distance matrix and 1/s of the tensor-core work (1/4 at the reference's default -stride 4).  When the caller
+# wants D2 / D3 and not D1 itself (the classic++ pipeline after compute_D1's own outputs: video_textures.py:265-284
+# uses P3_new only), K1 computes the s class matrices in ONE launch (job list over the clip viewed as [N/s, s*K]) and
+# K2 walks the planes round-robin in the same tap order, so D2 and D3 are bit-identical to the full-D1 path.
+RESIDUE_FAST = {(40, 4), (16, 4)}          # (fs, stride) pairs with a register-resident K2 instantiation
+
+
+def residue_eligible(pf: PackedFrames, filter_size: int, stride: int) -> bool:
+    n = pf.packed.shape[0]
+    kb = pf.packed.shape[1] if pf.signed else pf.k
+    return ((filter_size, stride) in RESIDUE_FAST and n % stride == 0 and n // stride >= 1 and kb % 128 == 0
+            and pf.packed.stride(0) == kb and pf.packed.stride(1) == 1)
+
+
+def gram_l2_residues(pf: PackedFrames, stride: int) -> torch.Tensor:
+    """K1 on the residue classes: returns D1r [stride, N/stride, ld] fp32 with
+    D1r[r, a, b] = d(frame stride*a + r, frame stride*b + r), every plane symmetric.  One launch."""
+    n = pf.packed.shape[0]
+    nc = n // stride
+    kb = pf.packed.shape[1] if pf.signed else pf.k
+    ldc = (nc + 31) // 32 * 32
+    D1r = torch.empty((stride, nc, ldc), dtype=torch.float32, device=pf.packed.device)
+    jobs = []
+    for r in range(stride):
+        ptr = D1r.data_ptr() + r * nc * ldc * 4
+        jobs.append(dict(row0=0, rows=nc, col0=0, cols=nc, symmetric=1, count_stats=0, D=ptr, d_row0=0, ldd=ldc,
+                         DT=ptr, dt_row0=0, ldt=ldc, k_off=r * kb, sq_off=r, sq_stride=stride))
+    gram_l2_jobs(pf, jobs, n=nc, ld=stride * kb)
+    return D1r
+
+
+def diag_filter_residues(D1r: torch.Tensor, n_frames: int, filter_size: int, stride: int, p: float | None = None,
+                         stats: torch.Tensor | None = None, taps: np.ndarray | None = None, symmetric: bool | None = None,
+                         a0: int = 0, rows_out: int | None = None, in_row0: int = 0):
+    """K2 on the residue-class planes of `gram_l2_residues`.  Returns (D2 [rows_out, M], D3 | None), bit-identical to
+    diag_filter on the full matrix.  Row shards: the planes hold class rows [in_row0, in_row0 + D1r.shape[1])."""
+    m = filtered_size(n_frames, filter_size, stride)
+    rows_out = m - a0 if rows_out is None else rows_out
+    whole = a0 == 0 and rows_out == m and in_row0 == 0
+    symmetric = whole if symmetric is None else symmetric
+    if symmetric and not whole:
+        raise ValueError("symmetric=True needs the whole matrix")
+    taps = binomial_taps(filter_size) if taps is None else np.ascontiguousarray(taps, dtype=np.float32)
+    D2 = empty_matrix(rows_out, m, D1r.device)
+    D3 = empty_matrix(rows_out, m, D1r.device) if p is not None else None
+    s, z = _stats_ptrs(stats)
+    _lib.call("avtex_diag_filter_pow_res", _lib.ptr(D1r), D1r.stride(1), D1r.stride(0), in_row0, D1r.shape[1],
+              taps.ctypes.data_as(C.POINTER(C.c_float)), filter_size, stride, a0, rows_out, m, _lib.ptr(D2), D2.stride(0),
+              _lib.ptr(D3), D3.stride(0) if D3 is not None else 0, C.c_float(_f32(p if p is not None else 1.0)), s, z,
+              1 if symmetric else 0, _dev(D1r), _stream(D1r))
+    if symmetric:
+        mark_symmetric(D2)
+    return D2, D3
+
+
+def distance_filter(frames: torch.Tensor, filter_size: int, stride: int, p: float | None = 0.7,
+                    stats: torch.Tensor | None = None, allow_residues: bool = True):
+    """frames -> (D2, D3, how) without handing out D1: K0 + K1 + K2 with the residue-class shortcut when the stride,
+    the clip and the filter allow it (`how` = "residues"), else the full distance matrix ("gram" / "direct")."""
+    if allow_residues and stride >= 2 and frames.dtype in (torch.uint8, torch.float32):
+        pf = pack_frames(frames)
+        if residue_eligible(pf, filter_size, stride):
+            D1r = gram_l2_residues(pf, stride)              # speculative: the exactness domain is checked right below
+            if pf.exact_ok:
+                D2, D3 = diag_filter_residues(D1r, frames.shape[0], filter_size, stride, p=p, stats=stats)
+                return D2, D3, "residues"
+    D1, how = pairwise_l2(frames if frames.dtype in (torch.uint8, torch.float32) else frames.float())
+    D2, D3 = diag_filter(D1, filter_size, stride, p=p, stats=stats)
+    return D2, D3, how
 
 
 # --------------------------------------------------------------------------- K3 / K4

@@ -28,8 +28,15 @@ def shard_equals_single(res, single: dict) -> dict:
     """`res`: a dist.ShardResult with sigma / P3 / P3_new filled.  Returns {quantity: bool}."""
     p = res.plan
     own = p.a1 - p.a0
+    if res.D1.dim() == 3:                     # residue-class planes [stride, class rows from a0, ld]
+        s_ = res.D1.shape[0]
+        nc = single["D1"].shape[0] // s_
+        d1_ok = all(torch.equal(res.D1[r, :, :nc], single["D1"][r::s_, r::s_][p.a0:p.a0 + res.D1.shape[1]])
+                    for r in range(s_))
+    else:
+        d1_ok = torch.equal(res.D1, single["D1"][p.r_lo:p.r_hi])
     return dict(
-        D1=torch.equal(res.D1, single["D1"][p.r_lo:p.r_hi]),
+        D1=d1_ok,
         D2=torch.equal(res.D2, single["D2"][p.a0:p.a1h]),
         D3n=torch.equal(res.D3_new, single["D3n"][p.a0:p.a1h]),
         sweeps=res.n_sweeps == single["fc"].n_sweeps,

@@ -455,6 +455,52 @@ def _walk_sharded(avdist, engine, res, workspace, wl, rank):
     return int(sum(v.nbytes for v in rows._cache.values()))
 
 
+def residue_step_record(frames, fs, stride, flush, steps=5, warm=2):
+    """The same pass (norms, distances, filter, converged future cost, finalize) through the RESIDUE-CLASS pipeline
+    (engine.distance_filter): a stride-s filter reads D1[i,j] only where i = j (mod s), so K1 computes the s class
+    Gram matrices (1/s of the pairs, one launch) and K2 walks the planes; D2 / D3 / D3_new are bit-identical to the
+    full-D1 pass (tests/test_gpu_classic.py::test_residue_class_pipeline_is_bit_identical), D1 / P1 are not produced.
+    Reported NEXT to the headline, never instead of it."""
+    from audio_video_textures_b200 import engine
+    names = ["norms", "gram_residues", "filter", "future_cost", "finalize"]
+
+    def one():
+        ev = _events(6)
+        ev[0].record()
+        pf = engine.pack_frames(frames)
+        ev[1].record()
+        D1r = engine.gram_l2_residues(pf, stride)
+        ev[2].record()
+        D2, D3 = engine.diag_filter_residues(D1r, frames.shape[0], fs, stride, p=0.7)
+        ev[3].record()
+        fc = engine.future_cost_fused(D3, 0.997)
+        ev[4].record()
+        engine.future_cost_finalize(D3, fc.mvec, 0.997)
+        ev[5].record()
+        torch.cuda.synchronize()
+        return ev[0].elapsed_time(ev[5]), [ev[i].elapsed_time(ev[i + 1]) for i in range(5)], fc.n_sweeps
+
+    pf = engine.pack_frames(frames)
+    if not (engine.residue_eligible(pf, fs, stride) and pf.exact_ok):
+        return {"eligible": False}
+    for _ in range(warm):
+        one()
+    ms, st = [], []
+    for _ in range(steps):
+        flush.fill_(1)
+        torch.cuda.synchronize()
+        t, s_, sweeps = one()
+        ms.append(t)
+        st.append(s_)
+    n = frames.shape[0]
+    step = float(np.mean(ms))
+    return {"eligible": True, "ms_per_step": step, "value": n * n / (step * 1e-3), "unit": "frame-pairs/s",
+            "stages_ms": {k: float(v) for k, v in zip(names, np.median(np.array(st), axis=0))}, "sweeps": int(sweeps),
+            "pairs_computed_fraction": 1.0 / (2 * stride),
+            "note": "frame-pairs/s counts all N^2 pairs of the clip as the headline does; the tensor cores evaluate "
+                    "N^2/(2*stride) of them (the residue classes, upper triangles). Same D2/D3/D3_new bits as the headline pass."}
+
+
 def c5_record(args, dev, rank, world, peaks):
     """configs[4] at THIS N: 100000 frames 64x64, -m 3 -fs 40 -stride 4 (M = 24991).  Strong scaling: the same
     clip at every N, rows sharded over the ranks (N = 1: the single-GPU path, D1 = 40 GB resident)."""
@@ -517,6 +563,12 @@ def c5_record(args, dev, rank, world, peaks):
     if world > 1:
         dist.all_reduce(tot, op=dist.ReduceOp.MAX)
         dist.all_reduce(stg, op=dist.ReduceOp.MAX)
+    residue = None
+    if world == 1:
+        try:
+            residue = residue_step_record(frames, fs, stride, flush, steps=3, warm=1)
+        except Exception as exc:
+            residue = {"error": f"{type(exc).__name__}: {exc}"}
     # end to end: pinned host clip -> device (1/G per rank + NVLink all-gather) -> pipeline incl. sigma3 / P3_new ->
     # survivor lists on the host
     host = frames.reshape(n, -1).cpu().pin_memory()
@@ -558,7 +610,7 @@ def c5_record(args, dev, rank, world, peaks):
     return {"workload": workload_name(wl), "n_gpus": world, "scaling": "strong", "steps": steps, "warmup": warm,
             "ms_per_step": step_ms, "value": n * n / (step_ms * 1e-3), "unit": "frame-pairs/s",
             "sweeps": int(sweeps), "M": engine.filtered_size(n, fs, stride),
-            "stages_ms_max_over_ranks": stages,
+            "stages_ms_max_over_ranks": stages, "residue_pipeline": residue,
             "e2e": {"ms_per_step": float(t_e2e.item()), "value": n * n / (float(t_e2e.item()) * 1e-3),
                     "h2d_bytes_per_step": int(host.numel()), "d2h_bytes_per_step": int(d2h),
                     "includes": "pinned host clip -> HBM, norms, Gram, filter, future cost, sigma3, P3, P3_new, the 900-frame "
@@ -767,6 +819,11 @@ def run_ours(args):
             hbm = hbm_rooflines(dev, peaks)
         cpu = {kk: vv for kk, vv in cpu_reference(wl, args.cpu_budget, D1_host).items() if kk != "wall_s"}
         cpu["unit"] = "frame-pairs/s"
+    if world == 1 and not args.skip_extra and stride >= 2:
+        try:
+            extra["residue_pipeline"] = residue_step_record(frames, fs, stride, flush, steps=max(5, args.steps // 2))
+        except Exception as exc:
+            extra["residue_pipeline"] = {"error": f"{type(exc).__name__}: {exc}"}
     state.clear()
     del frames
     torch.cuda.empty_cache()

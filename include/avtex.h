@@ -83,7 +83,7 @@ AVTEX_API int avtex_gram_l2_s8(const int8_t *packed, int64_t n, int64_t kp, cons
 AVTEX_API int avtex_gram_l2_u8(const uint8_t *frames, int64_t n, int64_t k, int64_t ld, const int64_t *sqnorm,
                      int64_t row0, int64_t rows, int symmetric, float *D, int64_t ldd,
                      double *sum, unsigned long long *nnz, int device, void *stream);
-/* General form (one launch, up to 16 rectangles): job j covers frames rows [row0, row0+rows) against
+/* General form (one launch, up to 32 rectangles): job j covers frames rows [row0, row0+rows) against
  * output columns [col0, col0+cols) and writes
  *     D [(r - d_row0)  * ldd + c] = d(r, c)      if D  != NULL   (direct)
  *     DT[(c - dt_row0) * ldt + r] = d(r, c)      if DT != NULL   (transposed)
@@ -101,6 +101,13 @@ typedef struct AvtexGramJob {
     float *DT;
     int64_t dt_row0, ldt;
     int symmetric, count_stats;
+    /* Residue-class jobs (stride-s pipelines, see avtex_diag_filter_pow_res).  A stride-s filter reads D1[i,j] only
+     * where i = j (mod s); those entries are the s Gram matrices of the frames of one residue class each.  With the
+     * clip viewed as [N/s, s*K] (row a = frames s*a .. s*a+s-1 concatenated; pass n = N/s, ld = s*K, k = K), class r
+     * is the K-byte column range starting at k_off = r*K of every row, and the norm of its row a is
+     * sqnorm[sq_off + a * sq_stride] with sq_off = r, sq_stride = s.  Zero-initialised fields mean the ordinary
+     * job (k_off = 0, norms sqnorm[a]).  K must be a multiple of 128 when k_off is used. */
+    int64_t k_off, sq_off, sq_stride;
 } AvtexGramJob;
 /* clock_probe (nullable, 2 x u64 on the device): CTA 0 writes the SM cycles (clock64) and the wall nanoseconds
  * (globaltimer) its first epilogue warp spent in the tile loop — their ratio is the SM clock the kernel really
@@ -163,6 +170,22 @@ AVTEX_API int avtex_diag_filter_pow(const float *D1, int64_t ld1, int64_t in_row
 AVTEX_API int avtex_diag_filter_pow_sym(const float *D1, int64_t ld1, int64_t n_rows, const float *h_w, int fs, int stride,
                               int64_t m, float *D2, int64_t ld2, float *D3, int64_t ld3, float p,
                               double *sum, unsigned long long *nnz, int device, void *stream);
+
+/* The same filter over RESIDUE-CLASS planes, for stride >= 2.  A stride-s filter reads D1[i,j] only where
+ * i = j (mod s); those entries are the s Gram matrices of the frames of one residue class each (see the k_off / sq_off
+ * fields of AvtexGramJob): D1r[r][a, b] = d(frame s*a + r, frame s*b + r), plane r at D1r + r * plane, leading dimension
+ * ld1.  In class coordinates the filter is a stride-1 filter of ceil(fs/s) taps per plane: the planes hold CLASS rows
+ * [in_row0, in_row0 + in_rows) (row shards pass their halo'd block, like avtex_diag_filter_pow) and at least
+ * ceil(((m-1)*s + fs) / s) columns.  The kernel walks a diagonal through the planes round-robin in the same tap order
+ * k = 0..fs-1, so D2 / D3 are bit-identical to avtex_diag_filter_pow on the full matrix while K1 computed 1/s of the
+ * pairs.  symmetric != 0 (whole matrix only): additionally use the upper-triangle form (every plane of a distance
+ * matrix is symmetric).  Register-resident (fs, stride) pairs only: (40,4), (16,4).
+ * replaces: classic/computeD1.py:47-96 + classic/computeD2.py:34-42 + classic/q_learning.py:34 when only D2 / D3
+ * (not D1 / P1) are consumed, as in classic/video_textures.py:265-284 for -m 3. */
+AVTEX_API int avtex_diag_filter_pow_res(const float *D1r, int64_t ld1, int64_t plane, int64_t in_row0, int64_t in_rows,
+                              const float *h_w, int fs, int stride, int64_t a0, int64_t rows_out, int64_t m,
+                              float *D2, int64_t ld2, float *D3, int64_t ld3, float p, double *sum,
+                              unsigned long long *nnz, int symmetric, int device, void *stream);
 /* out = D ** p elementwise (D >= 0, p > 0), same pow as the fused epilogue above.
  * replaces: `D3 = D2 ** p` of classic/q_learning.py:34 when D2 is handed in by the caller. */
 AVTEX_API int avtex_pow_matrix(const float *D, int64_t ld, int64_t rows, int64_t cols, float p, float *out,

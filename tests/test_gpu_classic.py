@@ -260,6 +260,43 @@ def test_diag_filter_symmetric_form_is_bit_identical(eng, fs, stride, n):
     assert not eng.known_symmetric(Dg)                      # modified in place: no longer trusted
 
 
+@pytest.mark.parametrize("fs,stride,n,hw", [(40, 4, 1000, 16), (16, 4, 516, 16), (40, 4, 44, 16), (40, 4, 2048, 16)])
+def test_residue_class_pipeline_is_bit_identical(eng, fs, stride, n, hw):
+    """Stride-s pipelines read D1[i,j] only where i = j (mod s): the s residue-class Gram matrices (one launch, 1/s of
+    the pairs) + the plane-walking filter must give the SAME bits as the full distance matrix + filter."""
+    gen = torch.Generator().manual_seed(n + fs)
+    base = torch.randint(0, 256, (1, hw, hw, 3), dtype=torch.uint8, generator=gen)
+    drift = torch.randint(-20, 21, (n, hw, hw, 3), generator=gen)
+    frames = (base.int() + torch.cumsum(drift, 0) // 8).clamp(0, 255).to(torch.uint8).cuda()   # K = hw*hw*3: 768 / 192... 
+    pf = eng.pack_frames(frames)
+    if not eng.residue_eligible(pf, fs, stride):
+        pytest.skip("clip not eligible (K % 128)")
+    D1 = eng.gram_l2(pf)
+    st_f, st_r = eng.new_stats("cuda"), eng.new_stats("cuda")
+    F2, F3 = eng.diag_filter(D1, fs, stride, p=0.7, stats=st_f, symmetric=False)
+    D1r = eng.gram_l2_residues(pf, stride)
+    for r in range(stride):
+        nc = n // stride
+        assert torch.equal(D1r[r, :, :nc], D1[r::stride, r::stride])
+    for sym in (False, True):
+        st_r.zero_()
+        R2, R3 = eng.diag_filter_residues(D1r, n, fs, stride, p=0.7, stats=st_r, symmetric=sym)
+        assert torch.equal(R2, F2) and torch.equal(R3, F3), sym
+        (tf, zf), (tr, zr) = eng.read_stats(st_f), eng.read_stats(st_r)
+        assert zf == zr
+        np.testing.assert_allclose(tr, tf, rtol=1e-6)
+    m = F2.shape[0]
+    if m >= 12:                                           # row shard of the planes (class rows lo .. hi)
+        a0, rows = m // 3, m // 4
+        lo, hi = a0, a0 + rows - 1 + (fs - 1) // stride + 1
+        part, part3 = eng.diag_filter_residues(D1r[:, lo:hi], n, fs, stride, p=0.7, a0=a0, rows_out=rows, in_row0=lo)
+        assert torch.equal(part, F2[a0:a0 + rows]) and torch.equal(part3, F3[a0:a0 + rows])
+    D2, D3, how = eng.distance_filter(frames, fs, stride)
+    assert how == "residues" and torch.equal(D2, F2) and torch.equal(D3, F3)
+    D2b, _, how_b = eng.distance_filter(frames[:n - 1], fs, stride)                  # N % s != 0: full path
+    assert how_b == "gram" and D2b.shape[0] == eng.filtered_size(n - 1, fs, stride)
+
+
 def test_fused_pow_accuracy(eng):
     """D3 = D2 ** p is evaluated by a split-exponent exp2/log2 (common.cuh: pow_pos) instead of powf;
     it must stay within a few ulp of the exact power over the whole dynamic range, incl. 0."""

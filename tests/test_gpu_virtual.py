@@ -10,13 +10,13 @@ import torch
 pytestmark = pytest.mark.gpu
 
 
-def _check(n, h, w, fs, stride, world, calls=1):
+def _check(n, h, w, fs, stride, world, calls=1, residues=False):
     from audio_video_textures_b200 import dist as avd
     from audio_video_textures_b200 import engine, selfcheck
     from audio_video_textures_b200.classic.video_textures import texture_walk
     from audio_video_textures_b200.synth import synth_video
     frames = synth_video(n, h, w, seed=2).cuda()
-    box = avd.VirtualBox(n, fs, stride, world, frames.device)
+    box = avd.VirtualBox(n, fs, stride, world, frames.device, residues=residues)
     for _ in range(calls):
         results = box.step(frames, sigma_factor=4.5, threshold=0.08)
     torch.cuda.synchronize()
@@ -54,6 +54,15 @@ def test_virtual_ranks_repeated_calls_and_c5_shape():
     """8 ranks on the C5 layout (64x64 frames, -m 3) at a reduced frame count, three calls on the same buffers."""
     res = _check(6000, 64, 64, 40, 4, 8, calls=3)
     assert res[0].plan.m == 1491 and res[0].n_sweeps >= 2
+
+
+@pytest.mark.parametrize("world", [2, 8])
+@pytest.mark.parametrize("n,h,w,fs", [(1200, 16, 16, 40), (2052, 16, 8, 16), (6000, 64, 64, 40)])
+def test_virtual_ranks_residue_class_shards(n, h, w, fs, world):
+    """The sharded pipeline on residue-class planes (stride 4: K1 computes 1/4 of the pairs; 8 ranks x 4 classes = 32
+    Gram jobs in one launch, per-plane halos, the row-shard form of the plane-walking filter): every shard equals the
+    single-GPU FULL-D1 pipeline bit for bit, two calls on the same buffers."""
+    _check(n, h, w, fs, 4, world, calls=2, residues=True)
 
 
 def test_lazy_survivor_rows_equal_bulk_csr():
