@@ -501,6 +501,44 @@ def residue_step_record(frames, fs, stride, flush, steps=5, warm=2):
                     "N^2/(2*stride) of them (the residue classes, upper triangles). Same D2/D3/D3_new bits as the headline pass."}
 
 
+def sharded_residue_record(frames, n, fs, stride, rank, world, dev, flush, steps=5, warm=2):
+    """residue_step_record for N > 1: the row-sharded step on residue-class planes (dist.py, `residues=True`):
+    world x stride Gram jobs in one launch per rank, transposes pushed to the peers, per-plane halos."""
+    import torch.distributed as dist
+
+    from audio_video_textures_b200 import dist as avdist
+    ws = avdist.SymmetricShardWorkspace(n, fs, stride, rank, world, dev, residues=True)
+    names = ["norms", "gram", "filter", "future_cost", "finalize"]
+    for _ in range(warm):
+        avdist.classic_sharded(frames, fs, stride, rank, world, workspace=ws)
+    ms = []
+    for _ in range(steps):
+        flush.fill_(1)
+        torch.cuda.synchronize()
+        dist.barrier()
+        ev = _events(2)
+        ev[0].record()
+        avdist.classic_sharded(frames, fs, stride, rank, world, workspace=ws)
+        ev[1].record()
+        torch.cuda.synchronize()
+        ms.append(ev[0].elapsed_time(ev[1]))
+    runs = []
+    for _ in range(3):
+        flush.fill_(1)
+        torch.cuda.synchronize()
+        dist.barrier()
+        res = avdist.classic_sharded(frames, fs, stride, rank, world, workspace=ws, timing=True)
+        runs.append([res.stage_ms[k] for k in names])
+    t = torch.tensor([sum(ms)] + list(np.median(np.array(runs), axis=0)), dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    step = float(t[0].item()) / steps
+    return {"eligible": True, "ms_per_step": step, "value": n * n / (step * 1e-3), "unit": "frame-pairs/s",
+            "stages_ms_max_over_ranks": {k: float(v) for k, v in zip(names, t[1:].tolist())},
+            "sweeps": int(res.n_sweeps), "pairs_computed_fraction": 1.0 / (2 * stride),
+            "note": "row-sharded step on residue-class planes: the tensor cores evaluate N^2/(2*stride) pairs; same "
+                    "D2/D3/D3_new bits as the headline pass (extra.parity.residue_class_shards)"}
+
+
 def c5_record(args, dev, rank, world, peaks):
     """configs[4] at THIS N: 100000 frames 64x64, -m 3 -fs 40 -stride 4 (M = 24991).  Strong scaling: the same
     clip at every N, rows sharded over the ranks (N = 1: the single-GPU path, D1 = 40 GB resident)."""
@@ -564,11 +602,13 @@ def c5_record(args, dev, rank, world, peaks):
         dist.all_reduce(tot, op=dist.ReduceOp.MAX)
         dist.all_reduce(stg, op=dist.ReduceOp.MAX)
     residue = None
-    if world == 1:
-        try:
+    try:
+        if world == 1:
             residue = residue_step_record(frames, fs, stride, flush, steps=3, warm=1)
-        except Exception as exc:
-            residue = {"error": f"{type(exc).__name__}: {exc}"}
+        else:
+            residue = sharded_residue_record(frames, n, fs, stride, rank, world, dev, flush, steps=5, warm=2)
+    except Exception as exc:
+        residue = {"error": f"{type(exc).__name__}: {exc}"}
     # end to end: pinned host clip -> device (1/G per rank + NVLink all-gather) -> pipeline incl. sigma3 / P3_new ->
     # survivor lists on the host
     host = frames.reshape(n, -1).cpu().pin_memory()
@@ -637,7 +677,17 @@ def parity_record(dev, rank, world):
     flags = torch.tensor([int(ok[k]) for k in keys], device=dev)
     dist.all_reduce(flags, op=dist.ReduceOp.MIN)
     failed = [k for k, v in zip(keys, flags.tolist()) if not v]
+    # the residue-class shards (stride 4: 1/4 of the pairs) against the same single-GPU FULL-D1 pipeline
+    ws_r = avdist.SymmetricShardWorkspace(n, fs, stride, rank, world, dev, residues=True)
+    for _ in range(2):
+        res_r = avdist.classic_sharded(frames, fs, stride, rank, world, sigma_factor=4.5, threshold=0.08, workspace=ws_r)
+    ok_r = selfcheck.shard_equals_single(res_r, single)
+    flags = torch.tensor([int(ok_r[k]) for k in keys], device=dev)
+    dist.all_reduce(flags, op=dist.ReduceOp.MIN)
+    failed += ["residues:" + k for k, v in zip(keys, flags.tolist()) if not v]
     return {"status": "bit-exact" if not failed else "MISMATCH: " + ",".join(failed),
+            "residue_class_shards": "bit-exact against the full-D1 single-GPU pipeline" if not any(
+                f.startswith("residues:") for f in failed) else "MISMATCH",
             "clip": f"{n} frames 32x32, -fs {fs} -stride {stride}, M={res.plan.m}", "ranks": world,
             "checked": {"bit_exact": ["D1", "D2", "D3n", "sweeps", "survivors"], "rtol_1e-6": ["eps", "sigma"],
                         "rtol_1e-5": ["P3"]},
@@ -819,9 +869,13 @@ def run_ours(args):
             hbm = hbm_rooflines(dev, peaks)
         cpu = {kk: vv for kk, vv in cpu_reference(wl, args.cpu_budget, D1_host).items() if kk != "wall_s"}
         cpu["unit"] = "frame-pairs/s"
-    if world == 1 and not args.skip_extra and stride >= 2:
+    if not args.skip_extra and stride >= 2 and (world == 1 or (workspace is not None and n % stride == 0)):
         try:
-            extra["residue_pipeline"] = residue_step_record(frames, fs, stride, flush, steps=max(5, args.steps // 2))
+            if world == 1:
+                extra["residue_pipeline"] = residue_step_record(frames, fs, stride, flush, steps=max(5, args.steps // 2))
+            else:
+                extra["residue_pipeline"] = sharded_residue_record(frames, n, fs, stride, rank, world, dev, flush,
+                                                                   steps=max(5, args.steps // 2))
         except Exception as exc:
             extra["residue_pipeline"] = {"error": f"{type(exc).__name__}: {exc}"}
     state.clear()

@@ -6,7 +6,8 @@
   * future_cost_fused_kernel (cooperative, grid barrier between sweeps)
   * future_cost_fused_peer_kernel on 2 and 4 VIRTUAL ranks (flag barrier between concurrently resident kernels)
   * synthesis_step_kernel (dynamic row tickets + last-CTA selection, mapped pinned result)
-  * filter / finalize / probabilities / CSR compaction
+  * filter (general, symmetric-mirror and residue-plane forms) / finalize / probabilities / CSR compaction
+  * residue-class Gram jobs (k_off / strided norms, 4 symmetric jobs in one launch) and the 8-virtual-rank residue shards
 Results are checked against each other so a sanitizer-induced slowdown cannot hide a wrong answer."""
 import os
 import sys
@@ -44,6 +45,21 @@ for world in (2, 4):
     for r in res:
         ok = selfcheck.shard_equals_single(r, single)
         assert all(ok.values()), ok
+# symmetric filter form (shared-memory mirror tile) and the residue-class pipeline (K % 128 == 0, N % 4 == 0)
+S2, S3 = engine.diag_filter(D1, 16, 1, p=0.7, symmetric=True)
+assert torch.equal(S2, single["D2"]) and torch.equal(S3, single["D3"])
+fr4 = synth_video(776, 16, 8, seed=2).cuda()                   # K = 384
+pf4 = engine.pack_frames(fr4)
+full = engine.diag_filter(engine.gram_l2(pf4), 40, 4, p=0.7, symmetric=False)
+D1r = engine.gram_l2_residues(pf4, 4)
+for sym in (False, True):
+    R2, R3 = engine.diag_filter_residues(D1r, 776, 40, 4, p=0.7, symmetric=sym)
+    assert torch.equal(R2, full[0]) and torch.equal(R3, full[1])
+single4 = selfcheck.single_gpu_pipeline(fr4, 40, 4, 4.5, 0.08)
+box = avd.VirtualBox(776, 40, 4, 8, fr4.device, residues=True)
+for r in box.step(fr4, sigma_factor=4.5, threshold=0.08):
+    ok = selfcheck.shard_equals_single(r, single4)
+    assert all(ok.values()), ok
 emb = synth_embeddings(600, 96, seed=0).cuda()
 tn = engine.l2_normalize_rows(emb)
 ws = engine.SynthesisWorkspace(600, "cuda")

@@ -12,7 +12,15 @@ wl = dict(WORKLOADS[name])
 if len(sys.argv) > 3:
     wl["n"] = int(sys.argv[3])
 frames = synth_video_cuda(wl["n"], wl["h"], wl["w"], seed=0)
+residues = os.environ.get("AVTEX_STAGE_RESIDUES") == "1"       # the residue-class pipeline instead of the full D1
 for _ in range(reps):
+    if residues:
+        D2, D3, how = engine.distance_filter(frames, wl["fs"], wl["stride"], p=0.7)
+        assert how == "residues"
+        fc = engine.future_cost_fused(D3, 0.997)
+        D3n = engine.future_cost_finalize(D3, fc.mvec, 0.997)
+        torch.cuda.synchronize()
+        continue
     pf = engine.pack_frames(frames)
     D1 = engine.gram_l2(pf, stats=engine.new_stats(frames.device))
     D2, D3 = engine.diag_filter(D1, wl["fs"], wl["stride"], p=0.7)

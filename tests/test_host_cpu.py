@@ -158,8 +158,28 @@ def test_shard_plan_covers_rows_and_halos(n, fs, stride, world):
     assert owned == list(range(m))
 
 
+@pytest.mark.parametrize("n,fs,stride,world", [(5000, 40, 4, 8), (100000, 40, 4, 8), (7072, 40, 4, 2), (2052, 16, 4, 3)])
+def test_residue_class_shard_geometry(n, fs, stride, world):
+    """The residue-class shards are planned in CLASS coordinates (N/s frames, fs/s taps, stride 1) by the same
+    planner: output row ranges must coincide with the full plan's, the class rows held must cover what the
+    plane-walking filter reads, and the buffer must stack `stride` planes."""
+    from audio_video_textures_b200 import dist as avd
+    for r in range(world):
+        pb = avd.PeerBuffers(n, fs, stride, r, world, "cpu", residues=True)
+        p, c = pb.plan, pb.cplans[r]
+        assert (c.m, c.a0, c.a1, c.a1h) == (p.m, p.a0, p.a1, p.a1h)
+        assert c.r_lo == p.a0 and c.r_hi >= (p.a1h - 1) + (fs - 1) // stride + 1        # last class row read + 1
+        assert c.r_hi <= n // stride
+        assert pb.rows_max == stride * pb.rows_c and pb.ld % 32 == 0 and pb.ld >= n // stride
+    with pytest.raises(ValueError):
+        avd.PeerBuffers(n + 1, fs, stride, 0, world, "cpu", residues=True)               # N % stride != 0
+    with pytest.raises(ValueError):
+        avd.PeerBuffers(n, fs, 1, 0, world, "cpu", residues=True)                        # stride 1: nothing to skip
+
+
 @pytest.mark.parametrize("n,fs,stride,world", [(7072, 40, 4, 2), (12000, 40, 4, 8), (2051, 40, 4, 3), (333, 16, 1, 2),
-                                               (300, 40, 1, 8), (100000, 40, 4, 8)])
+                                               (300, 40, 1, 8), (100000, 40, 4, 8),
+                                               (25000, 10, 1, 8), (1768, 10, 1, 2)])        # last two: class coordinates
 def test_symmetric_shard_jobs_cover_every_needed_element_once(n, fs, stride, world):
     """Host logic of the peer-push scheme (no GPU, no process group): over all ranks, the direct and the
     transposed destinations of the job lists cover every (row, col) of every rank's CORE rows exactly once, and
