@@ -10,7 +10,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libavtex.so")
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 _p = C.c_void_p
 _i64 = C.c_int64

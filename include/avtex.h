@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define AVTEX_ABI_VERSION 2
+#define AVTEX_ABI_VERSION 3
 #if defined(__GNUC__)
 #define AVTEX_API __attribute__((visibility("default")))
 #else
