@@ -297,6 +297,25 @@ def test_residue_class_pipeline_is_bit_identical(eng, fs, stride, n, hw):
     assert how_b == "gram" and D2b.shape[0] == eng.filtered_size(n - 1, fs, stride)
 
 
+@pytest.mark.parametrize("stride,residues", [(4, True), (4, False), (1, False)])
+def test_pipeline_graph_replays_equal_eager(eng, stride, residues):
+    """engine.PipelineGraph: the whole pass captured in one CUDA graph; replays on different clips must equal the
+    eager pipeline bit for bit (D2, D3, D3_new, sweep count, eps trail, sigma statistics)."""
+    from audio_video_textures_b200 import selfcheck
+    from audio_video_textures_b200.synth import synth_video
+    n, h, w, fs = 600, 16, 16, 16
+    g = eng.PipelineGraph(n, h * w * 3, fs, stride, residues=residues)
+    assert g.how == ("residues" if residues else "gram")
+    for seed in (1, 2, 1):
+        frames = synth_video(n, h, w, seed=seed).cuda()
+        single = selfcheck.single_gpu_pipeline(frames, fs, stride, 4.5, 0.08)
+        g(frames)
+        assert torch.equal(g.D2, single["D2"]) and torch.equal(g.D3, single["D3"]) and torch.equal(g.D3_new, single["D3n"])
+        assert g.n_sweeps == single["fc"].n_sweeps and g.eps_trail == single["fc"].eps_trail
+        sigma = eng.sigma_from_stats(*eng.read_stats(g.stats), 4.5)
+        np.testing.assert_allclose(float(sigma), float(single["sigma"]), rtol=1e-6)
+
+
 def test_fused_pow_accuracy(eng):
     """D3 = D2 ** p is evaluated by a split-exponent exp2/log2 (common.cuh: pow_pos) instead of powf;
     it must stay within a few ulp of the exact power over the whole dynamic range, incl. 0."""
