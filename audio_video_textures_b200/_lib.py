@@ -74,6 +74,8 @@ class GramJob(C.Structure):
 SIGNATURES["avtex_future_cost_fused_peer"] = [_p, _i64, _i64, _i64, _i64, _f32, _f32, _int, _int, _int,
                                               C.POINTER(_p), _i64, C.POINTER(_p), C.POINTER(_p), C.c_uint,
                                               _p, _p, _p, _p, _int, _int, _p]
+SIGNATURES["avtex_gram_l2_jobs_fused_norms"] = [_p, _i64, _i64, _i64, _i64, _i64, _p, _p, _p, C.POINTER(GramJob), _int, _p, _p,
+                                               _int, _p]
 SIGNATURES["avtex_gram_l2_jobs"] = [_p, _int, _i64, _i64, _i64, _p, C.POINTER(GramJob), _int, _p, _p, _p, _int, _p]
 
 _lib = None

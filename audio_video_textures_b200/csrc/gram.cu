@@ -83,6 +83,15 @@ struct GramArgs {
     int group_m;                        // schedule group (row-tiles) of the 2-CTA kernel
     int l2_hint;                        // TMA L2 policy of the operand loads: 0 none, 1 A evict_last, 2 A and B evict_last
     unsigned long long *clock_probe;    // nullable: [0] SM cycles, [1] ns spent by CTA 0's first epilogue warp
+    // K0 fused into this launch (2-CTA kernel, raw u8 frames): the epilogue warps have nothing to do until the first
+    // tiles' MMAs retire (0.43 ms at K = 150528), so they compute the norms meanwhile — norm_units byte rows of
+    // norm_len bytes, norm_pitch apart, results to norm_out (= sqnorm) / norm_max; norm_sync (zeroed by the caller)
+    // counts the warps that have finished, and no epilogue reads sqnorm before all of them have.
+    const uint8_t *norm_src;
+    int64_t norm_units, norm_len, norm_pitch;
+    int64_t *norm_out;
+    unsigned long long *norm_max;
+    unsigned int *norm_sync;
     GramJob jobs[MAX_JOBS];
 };
 
@@ -200,7 +209,8 @@ __device__ __forceinline__ void epilogue_tile(const GramArgs &args, const GramJo
     const int64_t row_end = job.row0 + job.rows, col_end = job.col0 + job.cols;
     const int64_t r = r0 + lane;
     const bool r_ok = r < row_end;
-    const uint32_t nr = r_ok ? (uint32_t)__ldg(args.sqnorm + job.sq_off + r * job.sq_stride) : 0u;
+    // __ldcg, not __ldg: with the fused norms the vector is written by other SMs during this very launch
+    const uint32_t nr = r_ok ? (uint32_t)__ldcg(args.sqnorm + job.sq_off + r * job.sq_stride) : 0u;
     int64_t rows_here = row_end - r0;                              // valid rows of this warp's 32
     if (rows_here > 32) rows_here = 32;
     const bool sym = job.symmetric != 0;
@@ -221,7 +231,7 @@ __device__ __forceinline__ void epilogue_tile(const GramArgs &args, const GramJo
         if (cbase >= col_end || rows_here <= 0) continue;
         if (sym && cbase + 31 < r0) continue;                     // whole chunk below the diagonal for this warp
         const uint32_t nc_lane = (cbase + lane < col_end)
-                                     ? (uint32_t)__ldg(args.sqnorm + job.sq_off + (cbase + lane) * job.sq_stride) : 0u;
+                                     ? (uint32_t)__ldcg(args.sqnorm + job.sq_off + (cbase + lane) * job.sq_stride) : 0u;
         // warp-uniform: all 32 x 32 elements are valid and (symmetric) strictly above the diagonal ->
         // no per-element predicates (the per-element branches of the general path were the critical path
         // of the whole kernel at K = 12288: the epilogue, not the MMAs, set the tile time)
@@ -617,6 +627,63 @@ int count_tiles2(int TM, int TN, int symmetric, int GROUP_M2 = GROUP_M2_DEFAULT)
     return total;
 }
 
+// 16 raw bytes: sum of squares and sum (for the centred norm) by dp4a
+__device__ __forceinline__ void norm_accum16(const uint4 v, unsigned long long &sq, unsigned long long &sm) {
+    unsigned int q = 0, t = 0;
+    q = __dp4a(v.x, v.x, q); q = __dp4a(v.y, v.y, q); q = __dp4a(v.z, v.z, q); q = __dp4a(v.w, v.w, q);
+    t = __dp4a(v.x, 0x01010101u, t); t = __dp4a(v.y, 0x01010101u, t);
+    t = __dp4a(v.z, 0x01010101u, t); t = __dp4a(v.w, 0x01010101u, t);
+    sq += q;
+    sm += t;
+}
+
+// K0 inside K1 (see GramArgs): epilogue warp `ew` of `EW` takes the byte rows ew, ew + EW, ...; one warp streams one
+// row with 8 x 512 B in flight.  Returns when EVERY epilogue warp of the grid has published its norms (all CTAs of
+// this persistent launch are co-resident: one per SM).
+__device__ __forceinline__ void fused_norms(const GramArgs &args, int ew, int EW, int lane) {
+    unsigned long long wmax = 0;
+    const int64_t len = args.norm_len, kv = len & ~int64_t(15);
+    for (int64_t u = ew; u < args.norm_units; u += EW) {
+        const uint8_t *src = args.norm_src + u * args.norm_pitch;
+        unsigned long long sq = 0, sm = 0;
+        int64_t c = int64_t(lane) * 16;
+        for (; c + 7 * 512 < kv; c += 8 * 512) {
+            uint4 v[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = __ldg(reinterpret_cast<const uint4 *>(src + c + i * 512));
+#pragma unroll
+            for (int i = 0; i < 8; ++i) norm_accum16(v[i], sq, sm);
+        }
+        for (; c < kv; c += 512) norm_accum16(__ldg(reinterpret_cast<const uint4 *>(src + c)), sq, sm);
+        for (int64_t t = kv + lane; t < len; t += 32) {
+            const unsigned int x = src[t];
+            sq += x * x;
+            sm += x;
+        }
+        sq = warp_sum(sq);
+        sm = warp_sum(sm);
+        if (lane == 0) {
+            args.norm_out[u] = (int64_t)sq;
+            const unsigned long long centred = sq + 16384ull * (unsigned long long)len - 256ull * sm;
+            wmax = centred > wmax ? centred : wmax;
+        }
+    }
+    if (lane == 0) {
+        if (args.norm_max != nullptr && wmax != 0) atomicMax(args.norm_max, wmax);
+        __threadfence();
+        atomicAdd(args.norm_sync, 1u);
+        const long long t0 = clock64();
+        while (*reinterpret_cast<volatile unsigned int *>(args.norm_sync) < (unsigned int)EW) {
+            if (clock64() - t0 > 8000000000LL) {
+                printf("avtex gram: fused-norms barrier timeout (block %d)\n", blockIdx.x);
+                __trap();
+            }
+        }
+        __threadfence();
+    }
+    __syncwarp();
+}
+
 template <int ST>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS2, 1)
 gram_l2_s8_2cta_kernel(const __grid_constant__ CUtensorMap map, const GramArgs args) {
@@ -718,6 +785,7 @@ gram_l2_s8_2cta_kernel(const __grid_constant__ CUtensorMap map, const GramArgs a
         long long c0 = 0;
         unsigned long long g0 = 0;
         if (probe) { c0 = clock64(); asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g0)); }
+        if (args.norm_src != nullptr) fused_norms(args, int(blockIdx.x) * EPI_WARPS2 + (warp - 2), int(gridDim.x) * EPI_WARPS2, lane);
         TileCursor cur;
         for (int t = cluster_id; t < args.num_tiles; t += num_clusters) {
             int tm, tn, lt;
@@ -779,9 +847,16 @@ int make_map(EncodeTiledFn enc, CUtensorMap *map, const void *base, int64_t n, i
     return 0;
 }
 
+struct NormFusion {
+    int64_t units = 0, pitch = 0;              // units == 0: norms are already in sqnorm
+    unsigned long long *max_centred = nullptr;
+    unsigned int *sync = nullptr;
+};
+
 int launch_gram_jobs(const void *operand, bool is_signed, int64_t n, int64_t k_extent, int64_t pitch,
                      const int64_t *sqnorm, const AvtexGramJob *jobs, int num_jobs, double *sum,
-                     unsigned long long *nnz, unsigned long long *clock_probe, int device, void *stream) {
+                     unsigned long long *nnz, unsigned long long *clock_probe, int device, void *stream,
+                     const NormFusion &nf = NormFusion()) {
     AVTEX_ENTER(device);
     AVTEX_REQUIRE(n >= 1 && n < (int64_t(1) << 30) && k_extent >= 1 && k_extent < (int64_t(1) << 31),
                   "gram_l2: bad shape n=%lld k=%lld", (long long)n, (long long)k_extent);
@@ -801,6 +876,16 @@ int launch_gram_jobs(const void *operand, bool is_signed, int64_t n, int64_t k_e
     a.idesc = make_idesc(bm, is_signed);
     a.num_jobs = num_jobs;
     a.clock_probe = clock_probe;
+    a.norm_src = nullptr; a.norm_units = 0; a.norm_len = 0; a.norm_pitch = 0; a.norm_out = nullptr; a.norm_max = nullptr;
+    a.norm_sync = nullptr;
+    if (nf.units > 0) {
+        AVTEX_REQUIRE(two_cta && !is_signed, "gram_l2: fused norms need the 2-CTA kernel and raw uint8 frames");
+        AVTEX_REQUIRE(nf.sync != nullptr && nf.pitch >= k_extent && nf.pitch % 16 == 0,
+                      "gram_l2: fused norms need a zeroed sync word and 16-byte aligned frame rows");
+        a.norm_src = static_cast<const uint8_t *>(operand);
+        a.norm_units = nf.units; a.norm_len = k_extent; a.norm_pitch = nf.pitch;
+        a.norm_out = const_cast<int64_t *>(sqnorm); a.norm_max = nf.max_centred; a.norm_sync = nf.sync;
+    }
     a.group_m = (k_extent <= 16384) ? 16 : GROUP_M2_DEFAULT;
     a.l2_hint = 0;
     int st_mode = 0;
@@ -912,6 +997,16 @@ extern "C" int avtex_gram_l2_jobs(const void *operand, int operand_signed, int64
                                   unsigned long long *nnz, unsigned long long *clock_probe, int device, void *stream) {
     return launch_gram_jobs(operand, operand_signed != 0, n, k, ld, sqnorm, h_jobs, num_jobs, sum, nnz, clock_probe, device,
                             stream);
+}
+
+extern "C" int avtex_gram_l2_jobs_fused_norms(const uint8_t *frames, int64_t n, int64_t k, int64_t ld, int64_t norm_units,
+                                              int64_t norm_pitch, int64_t *sqnorm, unsigned long long *max_centred,
+                                              unsigned int *sync_zeroed, const AvtexGramJob *h_jobs, int num_jobs,
+                                              double *sum, unsigned long long *nnz, int device, void *stream) {
+    AVTEX_REQUIRE(norm_units >= 1 && sqnorm != nullptr, "gram_l2 (fused norms): norm_units >= 1 and a sqnorm vector");
+    NormFusion nf;
+    nf.units = norm_units; nf.pitch = norm_pitch; nf.max_centred = max_centred; nf.sync = sync_zeroed;
+    return launch_gram_jobs(frames, false, n, k, ld, sqnorm, h_jobs, num_jobs, sum, nnz, nullptr, device, stream, nf);
 }
 
 extern "C" int avtex_gram_tile_schedule2(int TM, int TN, int symmetric, int *tm_out, int *tn_out, int capacity) {

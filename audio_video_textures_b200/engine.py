@@ -91,6 +91,7 @@ class PackedFrames:
     flags: torch.Tensor           # int64[2] on device: [non-byte values seen, max centred sqnorm]
     signed: bool = True
     _checked: tuple | None = None
+    norms_pending: bool = False   # raw uint8 frames whose norms the NEXT Gram launch computes itself (pack_frames(defer_norms=True))
 
     def validate(self):
         """(ok, reason): is the tensor-core Gram path exact for these frames?  One 16-byte D2H read,
@@ -115,8 +116,10 @@ class PackedFrames:
         return self.validate()[1]
 
 
-def pack_frames(frames: torch.Tensor) -> PackedFrames:
-    """K0.  frames: CUDA tensor [N, ...] uint8 or float (integer-valued 0..255).  No host sync."""
+def pack_frames(frames: torch.Tensor, defer_norms: bool = False) -> PackedFrames:
+    """K0.  frames: CUDA tensor [N, ...] uint8 or float (integer-valued 0..255).  No host sync.
+    defer_norms: for raw uint8 frames launch nothing now — the next gram_l2 / gram_l2_residues / gram_l2_jobs on the
+    result computes the norms inside the Gram launch (its epilogue warps are idle until the first tiles are done)."""
     x = frames.reshape(frames.shape[0], -1)
     if x.stride(-1) != 1:
         x = x.contiguous()
@@ -128,8 +131,9 @@ def pack_frames(frames: torch.Tensor) -> PackedFrames:
     mx = C.c_void_p(flags.data_ptr() + 8)
     if x.dtype == torch.uint8 and x.stride(0) % 16 == 0 and x.data_ptr() % 16 == 0:
         # raw bytes feed the tensor cores directly: only the norms are computed (one read of the frames)
-        _lib.call("avtex_frame_norms_u8", _lib.ptr(x), n, k, x.stride(0), _lib.ptr(sqnorm), mx, dev, st)
-        pf = PackedFrames(x, sqnorm, k, flags, signed=False)
+        if not defer_norms:
+            _lib.call("avtex_frame_norms_u8", _lib.ptr(x), n, k, x.stride(0), _lib.ptr(sqnorm), mx, dev, st)
+        pf = PackedFrames(x, sqnorm, k, flags, signed=False, norms_pending=bool(defer_norms))
         if kp * 128 * 128 < GRAM_MAX_SQNORM:
             pf._checked = (True, "")
         return pf
@@ -179,6 +183,13 @@ def gram_l2(pf: PackedFrames, row0: int = 0, rows: int | None = None, symmetric:
     if symmetric is None:
         symmetric = (row0 == 0 and rows == n)
     D = empty_matrix(rows, n, pf.packed.device) if out is None else out
+    if pf.norms_pending:                                   # norms computed inside this launch (job-list entry point)
+        gram_l2_jobs(pf, [dict(row0=row0, rows=rows, col0=0, cols=n, symmetric=1 if symmetric else 0, count_stats=1,
+                               D=D.data_ptr(), d_row0=row0, ldd=D.stride(0),
+                               DT=D.data_ptr() if symmetric else None, dt_row0=0, ldt=D.stride(0))], stats)
+        if symmetric:
+            mark_symmetric(D)
+        return D
     s, z = _stats_ptrs(stats)
     if pf.signed:
         _lib.call("avtex_gram_l2_s8", _lib.ptr(pf.packed), n, kp, _lib.ptr(pf.sqnorm), row0, rows,
@@ -203,9 +214,20 @@ def gram_l2_jobs(pf: PackedFrames, jobs: list, stats: torch.Tensor | None = None
         dst.DT, dst.dt_row0, dst.ldt = j.get("DT"), j.get("dt_row0", 0), j.get("ldt", 0)
         dst.symmetric, dst.count_stats = int(j.get("symmetric", 0)), int(j.get("count_stats", 0))
         dst.k_off, dst.sq_off, dst.sq_stride = j.get("k_off", 0), j.get("sq_off", 0), j.get("sq_stride", 1)
-    n = pf.packed.shape[0] if n is None else n             # n / ld overridden by the residue-class view [N/s, s*K]
+    frames_n = pf.packed.shape[0]
+    n = frames_n if n is None else n                       # n / ld overridden by the residue-class view [N/s, s*K]
     s, z = _stats_ptrs(stats)
     k_extent = pf.packed.shape[1] if pf.signed else pf.k
+    if pf.norms_pending:
+        if clock_probe is not None:
+            raise ValueError("clock_probe and deferred norms cannot be combined")
+        sync = torch.zeros(1, dtype=torch.int32, device=pf.packed.device)
+        _lib.call("avtex_gram_l2_jobs_fused_norms", _lib.ptr(pf.packed), n, k_extent,
+                  pf.packed.stride(0) if ld is None else ld, frames_n, pf.packed.stride(0), _lib.ptr(pf.sqnorm),
+                  C.c_void_p(pf.flags.data_ptr() + 8), _lib.ptr(sync), arr, len(jobs), s, z, _dev(pf.packed),
+                  _stream(pf.packed))
+        pf.norms_pending = False
+        return
     _lib.call("avtex_gram_l2_jobs", _lib.ptr(pf.packed), 1 if pf.signed else 0, n, k_extent,
               pf.packed.stride(0) if ld is None else ld,
               _lib.ptr(pf.sqnorm), arr, len(jobs), s, z, _lib.ptr(clock_probe), _dev(pf.packed), _stream(pf.packed))
@@ -609,7 +631,7 @@ class PipelineGraph:
         self._result = None
 
     def _run(self):
-        pf = pack_frames(self.frames)
+        pf = pack_frames(self.frames, defer_norms=True)    # K0 runs inside the Gram launch
         self.pf = pf
         if self.how == "residues":
             self.D1 = gram_l2_residues(pf, self.stride)

@@ -116,6 +116,19 @@ AVTEX_API int avtex_gram_l2_jobs(const void *operand, int operand_signed, int64_
                        const int64_t *sqnorm, const AvtexGramJob *h_jobs, int num_jobs, double *sum,
                        unsigned long long *nnz, unsigned long long *clock_probe, int device, void *stream);
 
+/* avtex_gram_l2_jobs with K0 FUSED into the launch (raw uint8 frames, 2-CTA kernel): the epilogue warps of the Gram
+ * kernel are idle until the first tiles' MMAs retire (0.43 ms at K = 150528), so they compute the norms meanwhile —
+ * `norm_units` byte rows of k bytes, `norm_pitch` bytes apart starting at `frames` (for the residue-class view
+ * [N/s, s*k]: norm_units = N, norm_pitch = k), written to sqnorm[0 .. norm_units) and, when max_centred != NULL
+ * (zeroed by the caller), the maximum centred norm raised there as avtex_frame_norms_u8 does.  No epilogue reads a
+ * norm before every warp of the grid has published its share (`sync_zeroed`: one uint32 the caller sets to 0).
+ * Saves the separate pass over the frames (0.11 ms of a 1.5 ms step at C2) and its launch.
+ * replaces: the same lines as avtex_frame_norms_u8 + avtex_gram_l2_jobs. */
+AVTEX_API int avtex_gram_l2_jobs_fused_norms(const uint8_t *frames, int64_t n, int64_t k, int64_t ld, int64_t norm_units,
+                                   int64_t norm_pitch, int64_t *sqnorm, unsigned long long *max_centred,
+                                   unsigned int *sync_zeroed, const AvtexGramJob *h_jobs, int num_jobs,
+                                   double *sum, unsigned long long *nnz, int device, void *stream);
+
 /* sqnorm[i] = sum_c frames[i,c]^2 (exact); max_centred (nullable, zeroed by the caller) receives
  * max_i sum_c (frames[i,c]-128)^2 via atomicMax.  HBM-bound: one read of the frames. */
 AVTEX_API int avtex_frame_norms_u8(const uint8_t *frames, int64_t n, int64_t k, int64_t ld, int64_t *sqnorm,

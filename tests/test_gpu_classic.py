@@ -316,6 +316,35 @@ def test_pipeline_graph_replays_equal_eager(eng, stride, residues):
         np.testing.assert_allclose(float(sigma), float(single["sigma"]), rtol=1e-6)
 
 
+@pytest.mark.parametrize("n,h,w", [(777, 12, 12), (1000, 16, 16), (2048, 8, 8), (300, 20, 28)])
+def test_norms_fused_into_the_gram_launch(eng, n, h, w):
+    """pack_frames(defer_norms=True): K0 runs inside the Gram launch (idle epilogue warps).  Norms, the centred
+    maximum, D1 (symmetric, row block, job list) and the residue-class planes must equal the separate-kernel path."""
+    from audio_video_textures_b200.synth import synth_video
+    frames = synth_video(n, h, w, seed=n).cuda()
+    ref = eng.pack_frames(frames)
+    D1 = eng.gram_l2(ref)
+    pf = eng.pack_frames(frames, defer_norms=True)
+    assert pf.norms_pending and not pf.signed
+    D1f = eng.gram_l2(pf)
+    assert not pf.norms_pending
+    assert torch.equal(pf.sqnorm, ref.sqnorm) and torch.equal(pf.flags, ref.flags)
+    assert torch.equal(D1f, D1) and eng.known_symmetric(D1f)
+    pf2 = eng.pack_frames(frames, defer_norms=True)
+    blk = eng.gram_l2(pf2, 100, 150)
+    assert torch.equal(blk, D1[100:250]) and torch.equal(pf2.sqnorm, ref.sqnorm)
+    if eng.residue_eligible(ref, 40, 4):
+        pf3 = eng.pack_frames(frames, defer_norms=True)
+        assert torch.equal(eng.gram_l2_residues(pf3, 4), eng.gram_l2_residues(ref, 4))
+        assert torch.equal(pf3.sqnorm, ref.sqnorm) and torch.equal(pf3.flags, ref.flags)
+    # black-vs-white frames: the centred maximum must flag the clip as outside the exact domain in both paths
+    bw = torch.zeros((64, 224, 224, 3), dtype=torch.uint8, device="cuda")
+    bw[::2] = 255
+    a, b = eng.pack_frames(bw), eng.pack_frames(bw, defer_norms=True)
+    eng.gram_l2(b)
+    assert torch.equal(a.flags, b.flags) and a.exact_ok == b.exact_ok
+
+
 def test_fused_pow_accuracy(eng):
     """D3 = D2 ** p is evaluated by a split-exponent exp2/log2 (common.cuh: pow_pos) instead of powf;
     it must stay within a few ulp of the exact power over the whole dynamic range, incl. 0."""
