@@ -32,6 +32,8 @@ jobs = [dict(row0=0, rows=400, col0=0, cols=400, symmetric=1, count_stats=0, D=p
         dict(row0=0, rows=400, col0=400, cols=377, symmetric=0, count_stats=0, D=ptr, d_row0=0, ldd=ld, DT=ptr, dt_row0=0, ldt=ld)]
 engine.gram_l2_jobs(pf, jobs)
 assert torch.equal(out, D1)
+pfd = engine.pack_frames(frames, defer_norms=True)             # K0 fused into the Gram launch (counter barrier)
+assert torch.equal(engine.gram_l2(pfd), D1) and torch.equal(pfd.sqnorm, pf.sqnorm)
 pfs = engine.pack_frames(frames.float())                       # centred s8 operand path
 assert torch.equal(engine.gram_l2(pfs), D1)
 single = selfcheck.single_gpu_pipeline(frames, 16, 1, 4.5, 0.08)
