@@ -337,6 +337,19 @@ def test_device_generator_reproduces_numpy_legacy_randint():
         assert a == np.random.randint(0, 1000) and b == np.random.rand()
 
 
+def test_walk_draw_is_numpy_choice():
+    """texture_walk draws with a[np.random.randint(0, len(a))]; the reference with np.random.choice(a)
+    (classic/video_textures.py:78): same value AND same generator state afterwards, for every list length."""
+    lists = [np.arange(n, dtype=np.int32) * 3 + 1 for n in (1, 2, 3, 5, 600, 1000, 7, 1, 33, 4096, 100000, 2 ** 16 + 1)]
+    np.random.seed(11)
+    a = [int(np.random.choice(x)) for x in lists * 40]
+    sa = np.random.get_state()
+    np.random.seed(11)
+    b = [int(x[np.random.randint(0, len(x))]) for x in lists * 40]
+    sb = np.random.get_state()
+    assert a == b and sa[2] == sb[2] and np.array_equal(sa[1], sb[1])
+
+
 def test_planned_steps_matches_the_loop():
     from audio_video_textures_b200.contrastive.validate import planned_steps
     for max_length, W, S, ssr in ((900, 15, 6, 1), (900, 20, 4, 1), (15, 15, 6, 1), (16, 15, 6, 1), (0, 15, 6, 1), (630, 15, 6, 2)):
