@@ -366,19 +366,28 @@ class RankStep:
     # -- K1: my tiles, transposes pushed into the peers' shards
     def gram(self):
         pb = self.pb
+        n, k = self.x.shape
+        # the job list depends on the plans, the shard pointers and K only: built once per workspace (building the
+        # dicts and the ctypes array took ~0.1 ms of host time per step, during which the GPU sat idle behind the
+        # short norms kernel)
+        cache = pb.__dict__.setdefault("_job_cache", {})
+        arr = cache.get(k)
         if not pb.residues:
-            engine.gram_l2_jobs(self.pf, symmetric_jobs(pb.plans, pb.rank, pb.d1_ptrs, pb.ld, pb.stride))
+            if arr is None:
+                arr = cache[k] = engine.gram_job_array(symmetric_jobs(pb.plans, pb.rank, pb.d1_ptrs, pb.ld, pb.stride))
+            engine.gram_l2_jobs(self.pf, arr)
             return
         # one job list per residue-class plane (the same symmetric split, in class rows), all in ONE launch
-        n, k = self.x.shape
         if k % 128 or self.x.stride(0) != k:
             raise engine._lib.AvtexError("residue-class shards need dense rows with K % 128 == 0")
-        plane_bytes = pb.rows_c * pb.ld * 4
-        jobs = []
-        for r in range(pb.stride):
-            for j in symmetric_jobs(pb.cplans, pb.rank, [b + r * plane_bytes for b in pb.d1_ptrs], pb.ld, 1):
-                jobs.append(dict(j, k_off=r * k, sq_off=r, sq_stride=pb.stride))
-        engine.gram_l2_jobs(self.pf, jobs, n=n // pb.stride, ld=pb.stride * k)
+        if arr is None:
+            plane_bytes = pb.rows_c * pb.ld * 4
+            jobs = []
+            for r in range(pb.stride):
+                for j in symmetric_jobs(pb.cplans, pb.rank, [b + r * plane_bytes for b in pb.d1_ptrs], pb.ld, 1):
+                    jobs.append(dict(j, k_off=r * k, sq_off=r, sq_stride=pb.stride))
+            arr = cache[k] = engine.gram_job_array(jobs)
+        engine.gram_l2_jobs(self.pf, arr, n=n // pb.stride, ld=pb.stride * k)
 
     def halo(self):
         pb = self.pb
