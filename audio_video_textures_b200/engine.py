@@ -370,27 +370,29 @@ def transition_probs(D: torch.Tensor, sigma, shift: int = 1, rows_out: int | Non
     return P, Pn, counts
 
 
-_PINNED: dict = {"ring": [None] * 4, "next": 0}
+_PINNED: dict = {"ring": [None] * 2, "next": 0}
 
 
 def _pinned(nbytes: int) -> torch.Tensor:
-    """Page-locked staging memory of at least nbytes from a ring of 4 cached buffers (grown geometrically): results
-    exported through it stay valid until the fourth following export."""
+    """Page-locked staging memory of at least nbytes from a ring of 2 cached buffers (grown geometrically, both sized
+    on the first call — a page-locked allocation costs ~6 ms): results exported through it stay valid until the
+    second following export."""
+    ring = _PINNED["ring"]
     i = _PINNED["next"]
-    _PINNED["next"] = (i + 1) % len(_PINNED["ring"])
-    buf = _PINNED["ring"][i]
-    if buf is None or buf.numel() < nbytes:
-        buf = torch.empty(max(nbytes, 2 * (buf.numel() if buf is not None else 0), 1 << 20), dtype=torch.uint8,
-                          pin_memory=True)
-        _PINNED["ring"][i] = buf
-    return buf
+    _PINNED["next"] = (i + 1) % len(ring)
+    if ring[i] is None or ring[i].numel() < nbytes:
+        size = max(nbytes, 2 * max((b.numel() for b in ring if b is not None), default=0), 1 << 20)
+        for j in range(len(ring)):
+            if ring[j] is None or ring[j].numel() < nbytes:
+                ring[j] = torch.empty(size, dtype=torch.uint8, pin_memory=True)
+    return ring[i]
 
 
 def csr_from_matrix(P: torch.Tensor, counts: torch.Tensor | None = None):
     """Ascending non-zero columns per row -> (rowptr int64 numpy, colidx int32 numpy).
     Matrices up to 16 MB (M <= 2048) are compacted into a full-capacity index buffer and brought to the host with
     ONE asynchronous copy into page-locked memory and one sync; the arrays returned are VIEWS of that page-locked
-    buffer (valid until the fourth following export — copy them to keep them longer).  Round 1 sized the list with an
+    buffer (valid until the second following export — copy them to keep them longer).  Round 1 sized the list with an
     `.item()`, copied it with a pageable `.cpu()` and again into numpy: 1.5 ms at C2, more than the whole device
     pass; a fresh 3 MB numpy copy alone costs 1 ms (page faults).  Larger matrices size the list first."""
     rows, cols = P.shape

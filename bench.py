@@ -896,7 +896,7 @@ def run_ours(args):
                 times.append(time.perf_counter() - t0)
             d2h = rowptr.nbytes + colidx.nbytes + 3 * 4
         state.update(P3n=P3n, counts=LAST["counts"])
-        t_e2e = float(np.mean(times))
+        t_e2e = float(np.median(times))          # median: one page-locked allocation or host hiccup is not the path
         includes = ("compute_D1+compute_D2+q_learning (P1,P2,P3,P3_new, sigmas) + survivor lists D2H + the "
                     f"{len(walk)}-frame -m {wl['m']} walk")
     else:
@@ -911,7 +911,7 @@ def run_ours(args):
             sync_all()
             if it >= args.warmup:
                 times.append(time.perf_counter() - t0)
-        t = torch.tensor([float(np.mean(times))], dtype=torch.float64, device=dev)
+        t = torch.tensor([float(np.median(times))], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         t_e2e = float(t.item())
         includes = ("each rank copies 1/G of the pinned host clip, NVLink all-gather replicates it; sharded norms / "
