@@ -12,8 +12,9 @@ Main line
           per-sweep row minima) is a peer store from inside the kernels (dist.py).
   One "step" = norms (K0) -> tcgen05 Gram + L2 epilogue (K1) -> diagonal filter + pow (K2) -> all future-cost
   sweeps in one cooperative kernel (K3) -> finalize (K4).  `value` is timed with the byte frames resident in
-  HBM: the K steps are enqueued back to back between ONE synchronize (+ barrier) on each side, every step with its
-  own CUDA-event pair on the stream and a 256 MB L2 flush in front of it (outside the pair); at N = 1 a step is one
+  HBM: at N = 1 the K steps are enqueued back to back between ONE synchronize on each side, every step with its
+  own CUDA-event pair on the stream and a 256 MB L2 flush in front of it (outside the pair); at N > 1 the ranks are
+  re-aligned (synchronize + barrier) before every step so that one rank's flush is not charged to its peers; at N = 1 a step is one
   CUDA-graph replay (engine.PipelineGraph, K0 fused into the Gram launch), the eager launches are reported as
   extra.eager.  `e2e` goes through the reference-named entry points from PINNED HOST frames and includes sigma3 / P3 /
   P3_new, the survivor lists the walk needs copied back to the host and the 900-frame walk itself — the SAME
@@ -539,11 +540,11 @@ def sharded_residue_record(frames, n, fs, stride, rank, world, dev, flush, steps
     names = ["norms", "gram", "filter", "future_cost", "finalize"]
     for _ in range(warm):
         avdist.classic_sharded(frames, fs, stride, rank, world, workspace=ws)
-    torch.cuda.synchronize()
-    dist.barrier()
     evs = []
-    for _ in range(steps):                               # enqueued back to back, one sync + barrier on each side
+    for _ in range(steps):                               # ranks re-aligned before every step (see run_ours)
         flush.fill_(1)
+        torch.cuda.synchronize()
+        dist.barrier()
         ev = _events(2)
         ev[0].record()
         avdist.classic_sharded(frames, fs, stride, rank, world, workspace=ws)
@@ -806,6 +807,11 @@ def run_ours(args):
         # Python per step, with the GPU idle behind it) to a 1.5 ms step.
         for _ in range(args.steps):
             flush.fill_(1)                      # L2 flush (256 MB > 126 MB L2) between timed steps
+            if world > 1:
+                # N > 1: ranks are re-aligned before every step.  Free-running ranks advance at the pace of the
+                # slowest one INCLUDING its in-stream flush, which the faster ranks' event pairs would then absorb as
+                # barrier wait inside the step (measured at 8 GPUs: 1.98 ms instead of 1.88).
+                sync_all()
             launches += one_step(True)
         sync_all()
         for ev in pending:
