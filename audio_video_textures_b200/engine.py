@@ -597,8 +597,10 @@ def distance_filter(frames: torch.Tensor, filter_size: int, stride: int, p: floa
     """frames -> (D2, D3, how) without handing out D1: K0 + K1 + K2 with the residue-class shortcut when the stride,
     the clip and the filter allow it (`how` = "residues"), else the full distance matrix ("gram" / "direct")."""
     if allow_residues and stride >= 2 and frames.dtype in (torch.uint8, torch.float32):
-        pf = pack_frames(frames)
-        if residue_eligible(pf, filter_size, stride):
+        pf = pack_frames(frames, defer_norms=True)          # raw uint8: the norms are computed inside the Gram launch
+        if not residue_eligible(pf, filter_size, stride):
+            pf = None                                       # (a deferred raw-uint8 pack has launched nothing)
+        if pf is not None:
             D1r = gram_l2_residues(pf, stride)              # speculative: the exactness domain is checked right below
             if pf.exact_ok:
                 D2, D3 = diag_filter_residues(D1r, frames.shape[0], filter_size, stride, p=p, stats=stats)
