@@ -150,6 +150,40 @@ def load_frames_sharded(host_frames: torch.Tensor, rank: int, world: int, device
     return full[:n]
 
 
+def load_frames_pushed(host_frames: torch.Tensor, ws: "SymmetricShardWorkspace", chunks: int = 4) -> torch.Tensor:
+    """load_frames_sharded without NCCL and without waiting for the whole slice: every rank copies its 1/G of the
+    pinned host clip in `chunks` pieces and, as each piece lands, PUSHES it into all peers' copies of the clip through
+    peer-mapped symmetric memory (plain device copies over NVLink, peers visited in rotated order), so the NVLink
+    replication runs underneath the PCIe transfer instead of after it.  Stream-ordered symmetric-memory barriers fence
+    the buffers: nobody writes into a peer that may still be reading the previous clip, nobody computes before every
+    push has landed.  Returns the [N, K] uint8 clip on this rank's device (a view of the symmetric buffer)."""
+    x = host_frames.reshape(host_frames.shape[0], -1)
+    n, k = x.shape
+    world, rank = ws.world, ws.rank
+    buf = ws.frames_buffer(n, k)
+    per = buf.shape[0] // world
+    lo, hi = rank * per, min(n, (rank + 1) * per)
+    main = torch.cuda.current_stream(ws.device)
+    ws._hdl_frames.barrier(channel=0)                   # every rank is done with the previous clip (stream-ordered)
+    ws._copy_stream.wait_stream(main)
+    ws._push_stream.wait_stream(main)
+    step = max(1, -(-(hi - lo) // chunks))
+    for c0 in range(lo, hi, step):
+        c1 = min(hi, c0 + step)
+        with torch.cuda.stream(ws._copy_stream):
+            buf[c0:c1].copy_(x[c0:c1], non_blocking=True)
+            landed = torch.cuda.Event()
+            landed.record(ws._copy_stream)
+        with torch.cuda.stream(ws._push_stream):
+            ws._push_stream.wait_event(landed)
+            for s_ in range(1, world):
+                ws._frame_peers[(rank + s_) % world][c0:c1].copy_(buf[c0:c1], non_blocking=True)
+    main.wait_stream(ws._copy_stream)
+    main.wait_stream(ws._push_stream)
+    ws._hdl_frames.barrier(channel=1)                   # all pushes of all ranks have landed
+    return buf[:n]
+
+
 def pack_frames_sharded(frames: torch.Tensor, rank: int, world: int, group=None) -> engine.PackedFrames:
     """K0 for the replicated clip, NCCL form: every rank computes the norms of 1/G of the frames and the [N]
     int64 vector is all-gathered.  (The symmetric-memory path pushes them from the kernel instead.)"""
@@ -307,6 +341,20 @@ class SymmetricShardWorkspace(PeerBuffers):
     def peer_d1_rows(self, r: int, row_off: int, rows: int) -> torch.Tensor:
         buf = self.hdl.get_buffer(r, (self.rows_max, self.ld), torch.float32)
         return buf[row_off:row_off + rows]
+
+    def frames_buffer(self, n: int, k: int) -> torch.Tensor:
+        """The replicated clip [N padded to world * ceil(N / world), K] uint8 in symmetric memory (allocated on first
+        use, collectively), plus every rank's view of every peer's copy (`_frame_peers`)."""
+        per = -(-n // self.world)
+        shape = (per * self.world, k)
+        if getattr(self, "_frames", None) is None or tuple(self._frames.shape) != shape:
+            import torch.distributed._symmetric_memory as symm_mem
+            self._frames = symm_mem.empty(shape, dtype=torch.uint8, device=self.device)
+            self._hdl_frames = symm_mem.rendezvous(self._frames, self.group.group_name)
+            self._frame_peers = [self._hdl_frames.get_buffer(r, shape, torch.uint8) for r in range(self.world)]
+            self._copy_stream = torch.cuda.Stream(self.device)
+            self._push_stream = torch.cuda.Stream(self.device)
+        return self._frames
 
     def p3n(self) -> torch.Tensor:
         """This rank's P3_new shard [shard, mpad] in symmetric memory (allocated on first use, collectively)."""

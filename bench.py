@@ -649,7 +649,8 @@ def c5_record(args, dev, rank, world, peaks):
         flush.fill_(1)
         sync_all()
         t0 = time.perf_counter()
-        dev_frames = avdist.load_frames_sharded(host, rank, world, dev)
+        dev_frames = (avdist.load_frames_pushed(host, ws) if ws is not None else
+                      avdist.load_frames_sharded(host, rank, world, dev))
         if world == 1:
             pf = engine.pack_frames(dev_frames)
             D1 = engine.gram_l2(pf)
@@ -910,7 +911,10 @@ def run_ours(args):
             flush.fill_(1)
             sync_all()
             t0 = time.perf_counter()
-            dev_frames = avdist.load_frames_sharded(host, rank, world, dev)     # 1/G over PCIe + NVLink all-gather
+            if workspace is not None:                                           # 1/G over PCIe, NVLink pushes underneath
+                dev_frames = avdist.load_frames_pushed(host, workspace)
+            else:
+                dev_frames = avdist.load_frames_sharded(host, rank, world, dev)  # 1/G over PCIe + NCCL all-gather
             res = avdist.classic_sharded(dev_frames, fs, stride, rank, world, sigma_factor=f, threshold=0.08,
                                          workspace=workspace)
             d2h = _walk_sharded(avdist, engine, res, workspace, wl, rank)
@@ -920,7 +924,8 @@ def run_ours(args):
         t = torch.tensor([float(np.median(times))], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         t_e2e = float(t.item())
-        includes = ("each rank copies 1/G of the pinned host clip, NVLink all-gather replicates it; sharded norms / "
+        includes = ("each rank copies 1/G of the pinned host clip and pushes every piece to its peers over NVLink as it "
+                    "lands (NCCL all-gather without symmetric memory); sharded norms / "
                     "Gram / filter / future cost; sigma3 (all-reduce), P3, P3_new; the 900-frame walk on rank 0 over "
                     "survivor lists read on demand from the owning ranks' shards (peer-mapped)")
     e2e = {"value": n * n / t_e2e, "unit": "frame-pairs/s", "h2d_bytes_per_step": int(host.numel()),

@@ -37,6 +37,14 @@ def main():
     np.random.seed(0)
     b = texture_walk((rp1, ci1), 1, 30, 5, stride, fs)
     ok["walk"] = a == b
+    if ws is not None:                                   # clip replication by NVLink pushes under the PCIe copy
+        host = frames.cpu().pin_memory()
+        for _ in range(2):
+            got = avd.load_frames_pushed(host, ws, chunks=3)
+            torch.cuda.synchronize()
+            ok["pushed_frames"] = ok.get("pushed_frames", True) and torch.equal(got, frames.reshape(n, -1))
+        res2 = avd.classic_sharded(got, fs, stride, rank, world, sigma_factor=f, threshold=th, workspace=ws)
+        ok["pushed_pipeline"] = torch.equal(res2.D3_new, res.D3_new)
     if ws is not None:                                   # one-sided lazy rows out of the peers' symmetric P3_new shards
         ws.barrier(2)
         if rank == 0:
