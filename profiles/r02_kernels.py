@@ -104,6 +104,17 @@ elif what == "gramsym":
     ops = 2.0 * tiles * 256 * 256 * 12288
     cfg = " ".join(f"{k}={os.environ[k]}" for k in ("AVTEX_GRAM_GROUP", "AVTEX_GRAM_HINT", "AVTEX_GRAM_ST") if k in os.environ)
     print(f"gramsym n={n} K=12288 [{cfg}]: {ms:.3f} ms  {ops / ms / 1e9:.0f} TOP/s executed ({tiles} tiles)")
+elif what == "gramfused":
+    # C2 Gram with K0 fused into the launch (norms by the idle epilogue warps) vs separate K0 + K1
+    frames = synth_video_cuda(5000, 224, 224, seed=0)
+    def sep():
+        return engine.gram_l2(engine.pack_frames(frames))
+    def fused():
+        return engine.gram_l2(engine.pack_frames(frames, defer_norms=True))
+    ms_s, D_s = timed(sep, reps=5)
+    ms_f, D_f = timed(fused, reps=5)
+    assert torch.equal(D_s, D_f)
+    print(f"gramfused C2: K0 + K1 separate {ms_s:.3f} ms; K0 inside K1 {ms_f:.3f} ms")
 elif what == "gramjobs":
     # job list of rank `me` of an 8-rank C5 step, run on ONE GPU: the peer destinations all point at one local scratch
     # shard, so the time is everything except the NVLink transport of the pushed tiles
