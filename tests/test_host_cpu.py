@@ -337,6 +337,41 @@ def test_device_generator_reproduces_numpy_legacy_randint():
         assert a == np.random.randint(0, 1000) and b == np.random.rand()
 
 
+def test_symmetric_provenance_registry():
+    """engine.known_symmetric: only the very tensor object that was marked, and only while nobody wrote to it."""
+    from audio_video_textures_b200 import engine
+    a = torch.zeros(8, 8)
+    assert not engine.known_symmetric(a)
+    engine.mark_symmetric(a)
+    assert engine.known_symmetric(a)
+    assert not engine.known_symmetric(a[:4]) and not engine.known_symmetric(a.clone())
+    a[0, 1] = 3.0                                           # in-place edit bumps torch's version counter
+    assert not engine.known_symmetric(a)
+    for _ in range(40):                                     # the registry is bounded and drops dead tensors
+        engine.mark_symmetric(torch.zeros(2, 2))
+    assert len(engine._SYMMETRIC) <= 16
+
+
+def test_residue_eligibility_and_job_array():
+    from audio_video_textures_b200 import engine, _lib
+    def pf(n, k, pitch=None, signed=False):
+        pitch = k if pitch is None else pitch
+        buf = torch.zeros(n * pitch, dtype=torch.int8 if signed else torch.uint8)
+        x = buf.as_strided((n, k), (pitch, 1))
+        return engine.PackedFrames(x, torch.zeros(n, dtype=torch.int64), k, torch.zeros(2, dtype=torch.int64), signed=signed)
+    assert engine.residue_eligible(pf(1000, 768), 40, 4) and engine.residue_eligible(pf(1000, 768), 16, 4)
+    assert not engine.residue_eligible(pf(1001, 768), 40, 4)          # N % stride
+    assert not engine.residue_eligible(pf(1000, 192), 40, 4)          # K % 128
+    assert not engine.residue_eligible(pf(1000, 768, pitch=784), 40, 4)   # padded rows: the [N/s, s*K] view needs dense rows
+    assert not engine.residue_eligible(pf(1000, 768), 40, 1) and not engine.residue_eligible(pf(1000, 768), 5, 2)
+    arr = engine.gram_job_array([dict(row0=1, rows=2, col0=3, cols=4, symmetric=0, count_stats=1, D=1000, d_row0=1, ldd=64,
+                                      DT=None, k_off=768, sq_off=3, sq_stride=4),
+                                 dict(row0=0, rows=8, col0=0, cols=8, symmetric=1, D=2000, ldd=32, DT=2000, ldt=32)])
+    assert isinstance(arr, _lib.C.Array) and len(arr) == 2
+    assert (arr[0].k_off, arr[0].sq_off, arr[0].sq_stride, arr[0].DT) == (768, 3, 4, None)
+    assert (arr[1].k_off, arr[1].sq_off, arr[1].sq_stride, arr[1].symmetric, arr[1].DT) == (0, 0, 1, 1, 2000)
+
+
 def test_walk_draw_is_numpy_choice():
     """texture_walk draws with a[np.random.randint(0, len(a))]; the reference with np.random.choice(a)
     (classic/video_textures.py:78): same value AND same generator state afterwards, for every list length."""
