@@ -106,6 +106,52 @@ __device__ __forceinline__ void sweep_row(const float *__restrict__ row, int64_t
         sweep_elem<USE_A, EPS, HAVE2>(row[s], USE_A ? ld_ca_f(mp + s) : 0.f, (EPS && HAVE2) ? ld_ca_f(mp2 + s) : 0.f, s, j, alpha, acc);
 }
 
+// One WARP per row (rows of a few KB, matrix L2-resident): lane-strided float4 loads, no block-level reduction.
+template <bool USE_A, bool EPS, bool HAVE2>
+__device__ __forceinline__ void sweep_row_warp(const float *__restrict__ row, int64_t m, int64_t j,
+                                               const float *__restrict__ mp, const float *__restrict__ mp2,
+                                               float alpha, SweepAcc &acc, int lane) {
+    const bool vec = ((reinterpret_cast<uintptr_t>(row) & 15) == 0);
+    const int64_t mv = vec ? (m & ~int64_t(3)) : 0;
+    int64_t k = int64_t(lane) * 4;
+    for (; k + 3 * 128 < mv; k += 4 * 128) {
+        const float4 v0 = ld_stream_f4(row + k), v1 = ld_stream_f4(row + k + 128), v2 = ld_stream_f4(row + k + 256),
+                     v3 = ld_stream_f4(row + k + 384);
+        sweep_vec4<USE_A, EPS, HAVE2>(v0, mp, mp2, k, j, alpha, acc);
+        sweep_vec4<USE_A, EPS, HAVE2>(v1, mp, mp2, k + 128, j, alpha, acc);
+        sweep_vec4<USE_A, EPS, HAVE2>(v2, mp, mp2, k + 256, j, alpha, acc);
+        sweep_vec4<USE_A, EPS, HAVE2>(v3, mp, mp2, k + 384, j, alpha, acc);
+    }
+    for (; k < mv; k += 128) sweep_vec4<USE_A, EPS, HAVE2>(ld_stream_f4(row + k), mp, mp2, k, j, alpha, acc);
+    for (int64_t s = mv + lane; s < m; s += 32)
+        sweep_elem<USE_A, EPS, HAVE2>(row[s], USE_A ? ld_ca_f(mp + s) : 0.f, (EPS && HAVE2) ? ld_ca_f(mp2 + s) : 0.f, s, j, alpha, acc);
+}
+
+// One pass of the small-matrix fused kernels over this CTA's rows, a warp per row.  At M = 1241 (C2: D3 = 6 MB, in L2)
+// a CTA-wide row left 3/4 of the threads without data and cost two block reductions per row; with a warp per row the
+// grid shrinks to M/8 CTAs, which also makes the grid barrier between the sweeps cheaper — that barrier, not the
+// data, is the cost of a 6 MB sweep.  `emit(j, min)` is called by lane 0 of the row's warp; returns the CTA's eps
+// numerator to every thread.
+template <bool USE_A, bool EPS, bool HAVE2, typename Emit>
+__device__ __forceinline__ double warp_rows_pass(const float *__restrict__ D3, int64_t ld, int64_t row0, int64_t rows,
+                                                 int64_t m, const float *mp, const float *mp2, float alpha, double *dred,
+                                                 Emit emit) {
+    const int lane = threadIdx.x & 31;
+    SweepAcc acc{INFINITY, 0.0};
+    for (int64_t jl = int64_t(blockIdx.x) * (ST / 32) + (threadIdx.x >> 5); jl < rows; jl += int64_t(gridDim.x) * (ST / 32)) {
+        const int64_t j = row0 + jl;
+        const float *row = D3 + jl * ld;
+        acc.mn = INFINITY;
+        if (!USE_A || j == 0) sweep_row_warp<false, false, false>(row, m, j, mp, mp2, alpha, acc, lane);
+        else sweep_row_warp<true, EPS, HAVE2>(row, m, j, mp, mp2, alpha, acc, lane);
+        float mn = acc.mn;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+        if (lane == 0) emit(j, mn);
+    }
+    return EPS ? block_reduce(acc.e, 0.0, OpAdd<double>(), dred) : 0.0;
+}
+
 // 6 CTAs per SM (<= 42 registers): with the compiler's own 51 this kernel fell from 0.31 to 0.40 ms per pass at M = 19961
 __global__ void __launch_bounds__(ST, 6)
 future_cost_sweep_kernel(const float *__restrict__ D3, int64_t ld, int64_t row0, int64_t m,
@@ -231,6 +277,47 @@ future_cost_fused_kernel(const float *__restrict__ D3, int64_t ld, int64_t m, fl
     if (blockIdx.x == 0 && threadIdx.x == 0) { info[0] = 0; info[1] = cur; }
 }
 
+// future_cost_fused_kernel for small (L2-resident) matrices: a warp per row (warp_rows_pass).  Same contract.
+__global__ void __launch_bounds__(ST)
+future_cost_fused_small_kernel(const float *__restrict__ D3, int64_t ld, int64_t m, float alpha, float eps_stop,
+                               int max_sweeps, float *mbuf, int64_t mpad, double *eps_trail, int *info, float *m_out) {
+    __shared__ double dred[32];
+    cg::grid_group grid = cg::this_grid();
+    float *buf[3] = {mbuf, mbuf + mpad, mbuf + 2 * mpad};
+    {
+        float *dst = buf[0];
+        warp_rows_pass<false, false, false>(D3, ld, 0, m, m, nullptr, nullptr, alpha, dred,
+                                            [dst](int64_t j, float v) { dst[j] = v; });
+    }
+    grid.sync();
+    int cur = 0, prev2 = -1;
+    for (int p = 1; p <= max_sweeps; ++p) {
+        const int out = 3 - cur - (prev2 < 0 ? (cur == 0 ? 1 : 0) : prev2);
+        const float *mp = buf[cur];
+        const float *mp2 = prev2 < 0 ? nullptr : buf[prev2];
+        float *dst = buf[out];
+        const double e_blk =
+            mp2 == nullptr ? warp_rows_pass<true, true, false>(D3, ld, 0, m, m, mp, mp2, alpha, dred,
+                                                               [dst](int64_t j, float v) { dst[j] = v; })
+                           : warp_rows_pass<true, true, true>(D3, ld, 0, m, m, mp, mp2, alpha, dred,
+                                                              [dst](int64_t j, float v) { dst[j] = v; });
+        if (threadIdx.x == 0 && e_blk != 0.0) atomicAdd(eps_trail + p, e_blk);
+        grid.sync();
+        const double num = *reinterpret_cast<volatile double *>(eps_trail + p);
+        const float eps = (float)(num / ((double)m * (double)m));
+        if (!(eps > eps_stop)) {
+            if (blockIdx.x == 0 && threadIdx.x == 0) { info[0] = p; info[1] = cur; }
+            if (m_out != nullptr)
+                for (int64_t k = int64_t(blockIdx.x) * ST + threadIdx.x; k < m; k += int64_t(gridDim.x) * ST)
+                    m_out[k] = __ldcg(buf[cur] + k);
+            return;
+        }
+        prev2 = cur;
+        cur = out;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) { info[0] = 0; info[1] = cur; }
+}
+
 // ------------------------------------------------------------------ multi-GPU fused future cost
 // Row-sharded version of future_cost_fused_kernel: every GPU runs one cooperative kernel over its own
 // rows; after each sweep the freshly computed row minima are PUSHED into every peer's copy of the
@@ -338,6 +425,51 @@ future_cost_fused_peer_kernel(const FcPeerArgs a) {
     if (blockIdx.x == 0 && threadIdx.x == 0) { a.info[0] = 0; a.info[1] = cur; }
 }
 
+// future_cost_fused_peer_kernel for small shards: a warp per row.  Same contract and exchange protocol.
+__global__ void __launch_bounds__(ST)
+future_cost_fused_peer_small_kernel(const FcPeerArgs a) {
+    __shared__ double dred[32];
+    cg::grid_group grid = cg::this_grid();
+    const float *local = a.mbuf[a.rank];
+    auto push = [&a](int buf, int64_t j, float v) {
+        for (int r = 0; r < a.world; ++r) a.mbuf[r][(int64_t)buf * a.mpad + j] = v;
+    };
+    warp_rows_pass<false, false, false>(a.D3, a.ld, a.row0, a.rows, a.m, nullptr, nullptr, a.alpha, dred,
+                                        [&push](int64_t j, float v) { push(0, j, v); });
+    if (!fc_peer_exchange(grid, a, 0, false)) return;
+    int cur = 0, prev2 = -1;
+    for (int p = 1; p <= a.max_sweeps; ++p) {
+        const int out = 3 - cur - (prev2 < 0 ? (cur == 0 ? 1 : 0) : prev2);
+        const float *mp = local + (int64_t)cur * a.mpad;
+        const float *mp2 = prev2 < 0 ? nullptr : local + (int64_t)prev2 * a.mpad;
+        const double e_blk =
+            mp2 == nullptr ? warp_rows_pass<true, true, false>(a.D3, a.ld, a.row0, a.rows, a.m, mp, mp2, a.alpha, dred,
+                                                               [&push, out](int64_t j, float v) { push(out, j, v); })
+                           : warp_rows_pass<true, true, true>(a.D3, a.ld, a.row0, a.rows, a.m, mp, mp2, a.alpha, dred,
+                                                              [&push, out](int64_t j, float v) { push(out, j, v); });
+        if (threadIdx.x == 0 && e_blk != 0.0) atomicAdd(a.eps_local + p, e_blk);
+        if (!fc_peer_exchange(grid, a, p, true)) return;
+        double num = 0.0;
+        for (int r = 0; r < a.world; ++r)
+            num += *reinterpret_cast<volatile double *>(a.epsbuf[a.rank] + (int64_t)p * a.world + r);
+        if (blockIdx.x == 0 && threadIdx.x == 0) a.eps_trail[p] = num;
+        const float eps = (float)(num / ((double)a.m * (double)a.m));
+        if (!(eps > a.eps_stop)) {
+            if (blockIdx.x == 0 && threadIdx.x == 0) { a.info[0] = p; a.info[1] = cur; }
+            if (a.m_out != nullptr)
+                for (int64_t k = int64_t(blockIdx.x) * ST + threadIdx.x; k < a.m; k += int64_t(gridDim.x) * ST)
+                    a.m_out[k] = __ldcg(mp + k);
+            return;
+        }
+        prev2 = cur;
+        cur = out;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) { a.info[0] = 0; a.info[1] = cur; }
+}
+
+// Rows of a few KB in an L2-sized matrix / shard: the warp-per-row kernels.
+inline bool fc_small(int64_t rows, int64_t m) { return m <= 8192 && rows * m * 4 <= (int64_t(96) << 20); }
+
 }  // namespace
 
 extern "C" int avtex_future_cost_sweep(const float *D3, int64_t ld, int64_t row0, int64_t rows, int64_t m,
@@ -384,14 +516,16 @@ extern "C" int avtex_future_cost_fused(const float *D3, int64_t ld, int64_t m, f
     if (int rc = avtex_device_info(device, &sms, &cc)) return rc;
     AVTEX_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device));
     AVTEX_REQUIRE(coop != 0, "future_cost_fused: device does not support cooperative launch");
-    AVTEX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, future_cost_fused_kernel, ST, 0));
+    const bool small = fc_small(m, m);
+    const void *kernel = small ? (const void *)future_cost_fused_small_kernel : (const void *)future_cost_fused_kernel;
+    AVTEX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, ST, 0));
     AVTEX_REQUIRE(per_sm >= 1, "future_cost_fused: kernel does not fit on an SM");
     int64_t grid = (int64_t)sms * per_sm;              // full occupancy: the sweeps are HBM/L2 streaming
-    if (grid > m) grid = m;
+    const int64_t work = small ? (m + ST / 32 - 1) / (ST / 32) : m;          // CTAs that have a row (or 8) to process
+    if (grid > work) grid = work;
     void *args[] = {(void *)&D3, (void *)&ld, (void *)&m, (void *)&alpha, (void *)&eps_stop, (void *)&max_sweeps,
                     (void *)&mbuf, (void *)&mpad, (void *)&eps_trail, (void *)&info, (void *)&m_out};
-    AVTEX_CUDA(cudaLaunchCooperativeKernel((void *)future_cost_fused_kernel, dim3((unsigned)grid), dim3(ST), args, 0,
-                                           as_stream(stream)));
+    AVTEX_CUDA(cudaLaunchCooperativeKernel(kernel, dim3((unsigned)grid), dim3(ST), args, 0, as_stream(stream)));
     return 0;
 }
 
@@ -421,16 +555,18 @@ extern "C" int avtex_future_cost_fused_peer(const float *D3, int64_t ld, int64_t
     if (int rc = avtex_device_info(device, &sms, &cc)) return rc;
     AVTEX_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device));
     AVTEX_REQUIRE(coop != 0, "future_cost_fused_peer: device does not support cooperative launch");
-    AVTEX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, future_cost_fused_peer_kernel, ST, 0));
+    const bool small = fc_small(rows, m);
+    const void *kernel = small ? (const void *)future_cost_fused_peer_small_kernel : (const void *)future_cost_fused_peer_kernel;
+    AVTEX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, ST, 0));
     AVTEX_REQUIRE(per_sm >= 1, "future_cost_fused_peer: kernel does not fit on an SM");
     int64_t grid = (int64_t)sms * per_sm;
     // max_ctas > 0: several ranks share ONE device ("virtual ranks", tests): their cooperative kernels must
     // all be resident at the same time or the flag barrier would never close
     if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
     if (max_ctas < 0) grid = grid / (-max_ctas) > 0 ? grid / (-max_ctas) : 1;      // -G: an equal share for each of G ranks
-    if (grid > rows) grid = rows;
+    const int64_t work = small ? (rows + ST / 32 - 1) / (ST / 32) : rows;
+    if (grid > work) grid = work;
     void *args[] = {(void *)&a};
-    AVTEX_CUDA(cudaLaunchCooperativeKernel((void *)future_cost_fused_peer_kernel, dim3((unsigned)grid), dim3(ST), args, 0,
-                                           as_stream(stream)));
+    AVTEX_CUDA(cudaLaunchCooperativeKernel(kernel, dim3((unsigned)grid), dim3(ST), args, 0, as_stream(stream)));
     return 0;
 }
